@@ -1,0 +1,46 @@
+// plan.h — the projection plan: host block layout + device descriptors + launch classes.
+#pragma once
+#include "common.h"
+#include "blocks.h"
+#include "project_jacobi.cuh"
+
+struct cuadmm_plan {
+    int device = -1;
+    cuadmm::BlockLayout layout;
+
+    // launch classes: blocks grouped by size range, each class = one kernel launch
+    struct Class {
+        int kind;          // index into the kernel table
+        int nmax;          // largest n in the class
+        int32_t count;     // blocks in the class
+        int64_t first;     // first descriptor (in d_desc)
+        size_t smem;       // dynamic shared memory per CTA
+        int grid;
+    };
+    std::vector<Class> classes;
+    std::vector<cuadmm::BlkDesc> h_desc;       // class-major, n descending inside a class
+    cuadmm::DevBuf<cuadmm::BlkDesc> d_desc;
+    cuadmm::DevBuf<double> d_scratch;          // global-memory Jacobi variant / large path
+    cuadmm::DevBuf<double> d_eig;              // debug eigenvalue output (sum n)
+    cuadmm::DevBuf<int32_t> d_sweeps;
+    cuadmm::DevBuf<double> d_in, d_out;        // staging for the *_host entry points
+    // pooled-layout descriptors for svec<->smat
+    cuadmm::DevBuf<int64_t> d_svec_off, d_mat_off;
+    cuadmm::DevBuf<int32_t> d_blk;
+    cuadmm::DevBuf<uint8_t> d_pool;
+
+    double threshold = 1e-11;
+    int max_sweeps = 40;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaStream_t> side_streams;    // classes run concurrently on these
+    std::vector<cudaEvent_t> side_events;
+    cudaEvent_t fork_event = nullptr;
+    double last_ms = 0.0;
+    int64_t last_launches = 0;
+
+    ~cuadmm_plan();
+    void build_device();
+    // core launcher; epi may be null.  Returns the number of kernel launches.
+    int project(const double* d_Xb, double* d_Xproj, cudaStream_t stream,
+                const cuadmm::ProjEpilogue* epi, bool want_eig);
+};

@@ -1,0 +1,728 @@
+// project.cu — PSD projection kernels (shared-memory one-sided Jacobi) and their launcher.
+// See project_jacobi.cuh for the algorithm; this file holds the kernels, the size classes
+// and the svec<->smat kernels on the reference's pooled layout.
+#include "plan.h"
+#include <algorithm>
+#include <numeric>
+
+namespace cuadmm {
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+template <bool WARP>
+__device__ __forceinline__ void mat_sync() {
+    if (WARP) __syncwarp(); else __syncthreads();
+}
+
+// sum over the NT threads working on one matrix; every thread receives the total
+template <int NT, bool WARP>
+__device__ __forceinline__ double mat_sum(double v, double* red, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (WARP) return v;
+    const int wid = tid >> 5;
+    __syncthreads();
+    if ((tid & 31) == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < NT / 32; ++i) t += red[i];   // same order in every thread => identical
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory kernel: T threads per CTA, L lanes per column pair, up to RPL rows per lane.
+// WARP = true: one warp per matrix, T/32 matrices per CTA.
+// ------------------------------------------------------------------------------------------
+template <int T, int L, int RPL, bool WARP>
+__global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
+    extern __shared__ double smem[];
+    constexpr int NT = WARP ? 32 : T;
+    constexpr int NG = NT / L;
+    constexpr int MPC = WARP ? T / 32 : 1;
+    const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x;
+    const int mat_in_cta = WARP ? (threadIdx.x >> 5) : 0;
+    const int bi = blockIdx.x * MPC + mat_in_cta;
+    if (bi >= a.nblk) return;
+
+    const int ldm = nmax | 1;
+    const size_t per_mat = (size_t)ldm * nmax + nmax + (nmax + 2) / 2 + 1 + 34;
+    double* G = smem + per_mat * mat_in_cta;
+    double* w = G + (size_t)ldm * nmax;
+    int* pos = (int*)(w + nmax);
+    double* red = w + nmax + (nmax + 2) / 2 + 1;
+
+    const BlkDesc d = a.desc[bi];
+    const int n = d.n;
+    const int ld = n | 1;
+    const int ntri = n * (n + 1) / 2;
+    const double* __restrict__ xin = a.Xb + d.svec_off;
+    double* __restrict__ xout = a.Xproj + d.svec_off;
+
+    // ---- svec -> smat (vector_to_matrices), Frobenius norm on the fly ----
+    double f2 = 0.0;
+    for (int idx = tid; idx < ntri; idx += NT) {
+        int r, c;
+        tri_unrank(idx, r, c);
+        const double v = xin[idx];
+        f2 += v * v;
+        const double v2 = (r == c) ? v : v * CUADMM_SQRT2INV;
+        G[r + c * ld] = v2;
+        G[c + r * ld] = v2;
+    }
+    f2 = mat_sum<NT, WARP>(f2, red, tid);
+    const double s = sqrt(f2);
+    if (!(s >= 1e-290)) {
+        // zero block (or NaN input): Pi_+(0) = 0; NaN propagates
+        const double fill = (s == s) ? 0.0 : s;
+        for (int idx = tid; idx < ntri; idx += NT) {
+            xout[idx] = fill;
+            if (a.epi.X) {
+                const int64_t gi = d.svec_off + idx;
+                const double sig = *a.epi.sig_ptr;
+                const double Sv = (fill - a.epi.X[gi]) / sig - a.epi.Rd1[gi];
+                a.epi.S[gi] = Sv;
+                a.epi.SmC[gi] = Sv - a.epi.Cd[gi];
+            }
+        }
+        if (tid == 0) {
+            if (a.sweeps_out) a.sweeps_out[d.index] = 0;
+        }
+        if (a.eig_out) for (int j = tid; j < n; j += NT) a.eig_out[d.w_off + j] = fill;
+        return;
+    }
+    const double inv_s = 1.0 / s;
+    mat_sync<WARP>();
+    // G <- A / s + I
+    for (int e = tid; e < n * n; e += NT) {
+        const int c = e / n, r = e - c * n;
+        const double v = G[r + c * ld] * inv_s;
+        G[r + c * ld] = (r == c) ? v + 1.0 : v;
+    }
+    mat_sync<WARP>();
+
+    // ---- Jacobi sweeps ----
+    const int m = n + (n & 1);
+    const int half = m >> 1;
+    const int grp = tid / L, lane = tid % L;
+    const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << ((tid & 31) / L * L));
+    const double thr2 = a.threshold * a.threshold;
+    int sweeps = 0;
+    while (sweeps < a.max_sweeps) {
+        int big = 0;
+        for (int step = 0; step < m - 1; ++step) {
+            for (int k = grp; k < half; k += NG) {
+                int pa, pb;
+                rr_pair(m, step, k, pa, pb);
+                if (pa >= n || pb >= n) continue;  // the bye of an odd-sized block
+                const int p = min(pa, pb), q = max(pa, pb);
+                double* __restrict__ Gp = G + p * ld;
+                double* __restrict__ Gq = G + q * ld;
+                double gp[RPL], gq[RPL];
+                double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) {
+                    const int r = lane + i * L;
+                    if (r < n) {
+                        gp[i] = Gp[r];
+                        gq[i] = Gq[r];
+                        al = fma(gp[i], gp[i], al);
+                        be = fma(gq[i], gq[i], be);
+                        ga = fma(gp[i], gq[i], ga);
+                    } else {
+                        gp[i] = 0.0; gq[i] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(gmask, al, o);
+                    be += __shfl_xor_sync(gmask, be, o);
+                    ga += __shfl_xor_sync(gmask, ga, o);
+                }
+                if (ga * ga > thr2 * al * be) big = 1;
+                double c, sn;
+                if (jacobi_cs(al, be, ga, c, sn)) {
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) {
+                        const int r = lane + i * L;
+                        if (r < n) {
+                            Gp[r] = c * gp[i] - sn * gq[i];
+                            Gq[r] = sn * gp[i] + c * gq[i];
+                        }
+                    }
+                }
+            }
+            mat_sync<WARP>();
+        }
+        ++sweeps;
+        const int any_big = WARP ? __any_sync(0xffffffffu, big) : __syncthreads_or(big);
+        if (!any_big) break;
+    }
+
+    // ---- eigenvalues from the column norms; weights of the positive part ----
+    for (int j = grp; j < n; j += NG) {
+        const double* Gj = G + j * ld;
+        double al = 0.0;
+        for (int r = lane; r < n; r += L) al = fma(Gj[r], Gj[r], al);
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) al += __shfl_xor_sync(gmask, al, o);
+        if (lane == 0) {
+            const double sigma = sqrt(al);
+            const double lam = s * (sigma - 1.0);
+            // sqrt of the rebuild weight: Pi_+ = sum_j w_j g_j g_j^T, w_j = lam_j / sigma_j^2
+            w[j] = (sigma > 1.0) ? sqrt(lam / al) : 0.0;
+            if (a.eig_out) a.eig_out[d.w_off + j] = lam;
+        }
+    }
+    mat_sync<WARP>();
+    if (tid == 0) {
+        int k = 0;
+        for (int j = 0; j < n; ++j) if (w[j] > 0.0) pos[k++] = j;
+        pos[n] = k;
+        if (a.sweeps_out) a.sweeps_out[d.index] = sweeps;
+    }
+    mat_sync<WARP>();
+    const int kpos = pos[n];
+    // h_j = sqrt(w_j) g_j for the positive columns
+    for (int e = tid; e < kpos * n; e += NT) {
+        const int jj = e / n, r = e - jj * n;
+        const int j = pos[jj];
+        G[r + j * ld] *= w[j];
+    }
+    mat_sync<WARP>();
+
+    // ---- rebuild + smat -> svec (matrices_to_vector), optional fused S / SmC ----
+    double sig = 1.0;
+    if (a.epi.X) sig = *a.epi.sig_ptr;
+    for (int idx = tid; idx < ntri; idx += NT) {
+        int r, c;
+        tri_unrank(idx, r, c);
+        double acc = 0.0;
+        for (int jj = 0; jj < kpos; ++jj) {
+            const double* Gj = G + pos[jj] * ld;
+            acc = fma(Gj[r], Gj[c], acc);
+        }
+        const double out = (r == c) ? acc : acc * CUADMM_SQRT2;
+        xout[idx] = out;
+        if (a.epi.X) {
+            const int64_t gi = d.svec_off + idx;
+            const double Sv = (out - a.epi.X[gi]) / sig - a.epi.Rd1[gi];
+            a.epi.S[gi] = Sv;
+            a.epi.SmC[gi] = Sv - a.epi.Cd[gi];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// global-memory variant for n > 168 (G lives in HBM/L2): same algorithm, one CTA of 1024
+// threads per block, one warp per column pair, rows streamed twice (dot, then update).
+// Correct for any n; the dense tridiagonal path supersedes it for large n.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) proj_jacobi_global_kernel(ProjArgs a) {
+    __shared__ double red[34];
+    __shared__ int s_k;
+    const int tid = threadIdx.x;
+    const int bi = blockIdx.x;
+    if (bi >= a.nblk) return;
+    const BlkDesc d = a.desc[bi];
+    const int n = d.n;
+    const int64_t ld = n;
+    const int64_t ntri = (int64_t)n * (n + 1) / 2;
+    double* G = a.scratch + d.scratch_off;          // n*n
+    double* w = G + (int64_t)n * n;                 // n
+    int* pos = (int*)(w + n);                       // n+1 ints
+    const double* __restrict__ xin = a.Xb + d.svec_off;
+    double* __restrict__ xout = a.Xproj + d.svec_off;
+
+    double f2 = 0.0;
+    for (int c = 0; c < n; ++c) {
+        const int64_t base = (int64_t)c * (c + 1) / 2;
+        for (int r = tid; r <= c; r += 1024) {
+            const double v = xin[base + r];
+            f2 += v * v;
+            const double v2 = (r == c) ? v : v * CUADMM_SQRT2INV;
+            G[r + c * ld] = v2;
+            G[c + r * ld] = v2;
+        }
+    }
+    f2 = mat_sum<1024, false>(f2, red, tid);
+    const double s = sqrt(f2);
+    if (!(s >= 1e-290)) {
+        const double fill = (s == s) ? 0.0 : s;
+        for (int64_t idx = tid; idx < ntri; idx += 1024) {
+            xout[idx] = fill;
+            if (a.epi.X) {
+                const int64_t gi = d.svec_off + idx;
+                const double sig = *a.epi.sig_ptr;
+                const double Sv = (fill - a.epi.X[gi]) / sig - a.epi.Rd1[gi];
+                a.epi.S[gi] = Sv;
+                a.epi.SmC[gi] = Sv - a.epi.Cd[gi];
+            }
+        }
+        if (tid == 0 && a.sweeps_out) a.sweeps_out[d.index] = 0;
+        if (a.eig_out) for (int j = tid; j < n; j += 1024) a.eig_out[d.w_off + j] = fill;
+        return;
+    }
+    const double inv_s = 1.0 / s;
+    __syncthreads();
+    for (int64_t e = tid; e < (int64_t)n * n; e += 1024) {
+        const int c = (int)(e / n), r = (int)(e - (int64_t)c * n);
+        const double v = G[e] * inv_s;
+        G[e] = (r == c) ? v + 1.0 : v;
+    }
+    __syncthreads();
+
+    const int m = n + (n & 1), half = m >> 1;
+    const int grp = tid >> 5, lane = tid & 31;
+    const double thr2 = a.threshold * a.threshold;
+    int sweeps = 0;
+    while (sweeps < a.max_sweeps) {
+        int big = 0;
+        for (int step = 0; step < m - 1; ++step) {
+            for (int k = grp; k < half; k += 32) {
+                int pa, pb;
+                rr_pair(m, step, k, pa, pb);
+                if (pa >= n || pb >= n) continue;
+                const int p = min(pa, pb), q = max(pa, pb);
+                double* Gp = G + p * ld;
+                double* Gq = G + q * ld;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int r = lane; r < n; r += 32) {
+                    const double x = Gp[r], y = Gq[r];
+                    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(0xffffffffu, al, o);
+                    be += __shfl_xor_sync(0xffffffffu, be, o);
+                    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                }
+                if (ga * ga > thr2 * al * be) big = 1;
+                double c, sn;
+                if (jacobi_cs(al, be, ga, c, sn)) {
+                    for (int r = lane; r < n; r += 32) {
+                        const double x = Gp[r], y = Gq[r];
+                        Gp[r] = c * x - sn * y;
+                        Gq[r] = sn * x + c * y;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        ++sweeps;
+        if (!__syncthreads_or(big)) break;
+    }
+    for (int j = grp; j < n; j += 32) {
+        const double* Gj = G + j * ld;
+        double al = 0.0;
+        for (int r = lane; r < n; r += 32) al = fma(Gj[r], Gj[r], al);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
+        if (lane == 0) {
+            const double sigma = sqrt(al);
+            const double lam = s * (sigma - 1.0);
+            w[j] = (sigma > 1.0) ? sqrt(lam / al) : 0.0;
+            if (a.eig_out) a.eig_out[d.w_off + j] = lam;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int k = 0;
+        for (int j = 0; j < n; ++j) if (w[j] > 0.0) pos[k++] = j;
+        s_k = k;
+        if (a.sweeps_out) a.sweeps_out[d.index] = sweeps;
+    }
+    __syncthreads();
+    const int kpos = s_k;
+    for (int64_t e = tid; e < (int64_t)kpos * n; e += 1024) {
+        const int jj = (int)(e / n), r = (int)(e - (int64_t)jj * n);
+        const int j = pos[jj];
+        G[r + j * ld] *= w[j];
+    }
+    __syncthreads();
+    double sig = 1.0;
+    if (a.epi.X) sig = *a.epi.sig_ptr;
+    for (int c = 0; c < n; ++c) {
+        const int64_t base = (int64_t)c * (c + 1) / 2;
+        for (int r = tid; r <= c; r += 1024) {
+            double acc = 0.0;
+            for (int jj = 0; jj < kpos; ++jj) {
+                const double* Gj = G + pos[jj] * ld;
+                acc = fma(Gj[r], Gj[c], acc);
+            }
+            const double out = (r == c) ? acc : acc * CUADMM_SQRT2;
+            xout[base + r] = out;
+            if (a.epi.X) {
+                const int64_t gi = d.svec_off + base + r;
+                const double Sv = (out - a.epi.X[gi]) / sig - a.epi.Rd1[gi];
+                a.epi.S[gi] = Sv;
+                a.epi.SmC[gi] = Sv - a.epi.Cd[gi];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// svec <-> smat on the reference's pooled layout (one CTA per block)
+// ------------------------------------------------------------------------------------------
+__global__ void svec_to_smat_kernel(const double* __restrict__ svec, double* large_mat, double* small_mat,
+                                    const int32_t* __restrict__ blk, const int64_t* __restrict__ svec_off,
+                                    const int64_t* __restrict__ mat_off, const uint8_t* __restrict__ pool) {
+    const int k = blockIdx.x;
+    const int n = blk[k];
+    const double* x = svec + svec_off[k];
+    double* M = (pool[k] ? small_mat : large_mat) + mat_off[k];
+    for (int c = blockIdx.y; c < n; c += gridDim.y) {
+        const int64_t base = (int64_t)c * (c + 1) / 2;
+        for (int r = threadIdx.x; r <= c; r += blockDim.x) {
+            // same arithmetic as vector_to_matrices_kernel: off-diagonals * SQRT2INV, mirror copied
+            const double v = (r == c) ? x[base + r] : x[base + r] * CUADMM_SQRT2INV;
+            M[(int64_t)n * c + r] = v;
+            M[(int64_t)n * r + c] = v;
+        }
+    }
+}
+
+__global__ void smat_to_svec_kernel(const double* __restrict__ large_mat, const double* __restrict__ small_mat,
+                                    double* svec, const int32_t* __restrict__ blk,
+                                    const int64_t* __restrict__ svec_off, const int64_t* __restrict__ mat_off,
+                                    const uint8_t* __restrict__ pool) {
+    const int k = blockIdx.x;
+    const int n = blk[k];
+    double* x = svec + svec_off[k];
+    const double* M = (pool[k] ? small_mat : large_mat) + mat_off[k];
+    for (int c = blockIdx.y; c < n; c += gridDim.y) {
+        const int64_t base = (int64_t)c * (c + 1) / 2;
+        for (int r = threadIdx.x; r <= c; r += blockDim.x) {
+            const double v = M[(int64_t)n * c + r];   // map_M1: column c, row r
+            x[base + r] = (r == c) ? v : v * CUADMM_SQRT2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// size classes
+// ------------------------------------------------------------------------------------------
+struct KernelClass {
+    int nmax_allowed;
+    int threads;
+    int mats_per_cta;
+    void (*fn)(ProjArgs, int);
+};
+
+static const KernelClass kClasses[] = {
+    {16, 128, 4, proj_jacobi_kernel<128, 4, 4, true>},
+    {32, 128, 1, proj_jacobi_kernel<128, 8, 4, false>},
+    {64, 512, 1, proj_jacobi_kernel<512, 16, 4, false>},
+    {96, 768, 1, proj_jacobi_kernel<768, 16, 6, false>},
+    {128, 1024, 1, proj_jacobi_kernel<1024, 16, 8, false>},
+    {168, 672, 1, proj_jacobi_kernel<672, 16, 11, false>},
+};
+static const int kNumSmemClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
+static const int kGlobalKind = kNumSmemClasses;
+
+static size_t smem_bytes(int nmax, int mats_per_cta) {
+    const size_t ldm = (size_t)(nmax | 1);
+    const size_t per_mat = ldm * nmax + nmax + (nmax + 2) / 2 + 1 + 34;
+    return per_mat * sizeof(double) * mats_per_cta;
+}
+
+}  // namespace cuadmm
+
+using namespace cuadmm;
+
+cuadmm_plan::~cuadmm_plan() {
+    if (device >= 0) {
+        cudaSetDevice(device);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (fork_event) cudaEventDestroy(fork_event);
+        for (auto s : side_streams) cudaStreamDestroy(s);
+        for (auto e : side_events) cudaEventDestroy(e);
+    }
+}
+
+void cuadmm_plan::build_device() {
+    const int64_t nblk = (int64_t)layout.blk.size();
+    // eigenvalue offsets in blk order
+    std::vector<int64_t> w_off(nblk + 1, 0);
+    for (int64_t k = 0; k < nblk; ++k) w_off[k + 1] = w_off[k] + layout.blk[k];
+
+    // classify
+    std::vector<std::vector<int64_t>> members(kNumSmemClasses + 1);
+    for (int64_t k = 0; k < nblk; ++k) {
+        const int n = layout.blk[k];
+        int kind = kGlobalKind;
+        for (int c = 0; c < kNumSmemClasses; ++c) if (n <= kClasses[c].nmax_allowed) { kind = c; break; }
+        members[kind].push_back(k);
+    }
+    h_desc.clear(); classes.clear();
+    int64_t scratch = 0;
+    // heaviest classes first so their launches start first
+    for (int kind = kNumSmemClasses; kind >= 0; --kind) {
+        auto& mem = members[kind];
+        if (mem.empty()) continue;
+        std::stable_sort(mem.begin(), mem.end(), [&](int64_t a, int64_t b) { return layout.blk[a] > layout.blk[b]; });
+        Class cl;
+        cl.kind = kind;
+        cl.nmax = layout.blk[mem[0]];
+        cl.count = (int32_t)mem.size();
+        cl.first = (int64_t)h_desc.size();
+        if (kind == kGlobalKind) {
+            cl.smem = 0;
+            cl.grid = cl.count;
+        } else {
+            cl.smem = smem_bytes(cl.nmax, kClasses[kind].mats_per_cta);
+            cl.grid = (cl.count + kClasses[kind].mats_per_cta - 1) / kClasses[kind].mats_per_cta;
+        }
+        for (int64_t k : mem) {
+            BlkDesc d;
+            d.svec_off = layout.svec_off[k];
+            d.w_off = w_off[k];
+            d.n = layout.blk[k];
+            d.index = (int32_t)k;
+            d.scratch_off = 0;
+            if (kind == kGlobalKind) {
+                d.scratch_off = scratch;
+                const int64_t n = d.n;
+                scratch += n * n + n + (n + 2) / 2 + 1;
+            }
+            h_desc.push_back(d);
+        }
+        classes.push_back(cl);
+    }
+    if (device < 0) return;
+
+    DeviceGuard g(device);
+    d_desc.upload(h_desc);
+    if (scratch) d_scratch.alloc(scratch);
+    d_eig.alloc(std::max<int64_t>(w_off[nblk], 1));
+    d_sweeps.alloc(std::max<int64_t>(nblk, 1));
+    d_svec_off.upload(layout.svec_off);
+    d_mat_off.upload(layout.mat_off);
+    d_blk.upload(layout.blk);
+    d_pool.upload(layout.pool);
+    CUADMM_CUDA(cudaEventCreate(&ev0));
+    CUADMM_CUDA(cudaEventCreate(&ev1));
+    CUADMM_CUDA(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+    for (size_t i = 1; i < classes.size(); ++i) {
+        cudaStream_t s; cudaEvent_t e;
+        CUADMM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CUADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        side_streams.push_back(s); side_events.push_back(e);
+    }
+    for (int c = 0; c < kNumSmemClasses; ++c) {
+        CUADMM_CUDA(cudaFuncSetAttribute((const void*)kClasses[c].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes(kClasses[c].nmax_allowed, kClasses[c].mats_per_cta)));
+    }
+    CUADMM_CUDA(cudaDeviceSynchronize());
+}
+
+int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t stream,
+                         const ProjEpilogue* epi, bool want_eig) {
+    if (device < 0) throw Error(CUADMM_ENODEVICE, "plan was built without a CUDA device; there is no CPU fallback");
+    int launches = 0;
+    // fork: class i>0 runs on its own stream so small and mid classes overlap
+    if (classes.size() > 1) CUADMM_CUDA(cudaEventRecord(fork_event, stream));
+    for (size_t i = 0; i < classes.size(); ++i) {
+        const Class& cl = classes[i];
+        cudaStream_t st = stream;
+        if (i > 0) {
+            st = side_streams[i - 1];
+            CUADMM_CUDA(cudaStreamWaitEvent(st, fork_event, 0));
+        }
+        ProjArgs a;
+        a.Xb = d_Xb; a.Xproj = d_Xproj;
+        a.desc = d_desc.p + cl.first;
+        a.nblk = cl.count;
+        a.threshold = threshold;
+        a.max_sweeps = max_sweeps;
+        a.eig_out = want_eig ? d_eig.p : nullptr;
+        a.sweeps_out = want_eig ? d_sweeps.p : nullptr;
+        a.scratch = d_scratch.p;
+        if (epi) a.epi = *epi; else { a.epi.X = nullptr; a.epi.Rd1 = nullptr; a.epi.Cd = nullptr; a.epi.S = nullptr; a.epi.SmC = nullptr; a.epi.sig_ptr = nullptr; }
+        if (cl.kind == kGlobalKind) {
+            proj_jacobi_global_kernel<<<cl.grid, 1024, 0, st>>>(a);
+        } else {
+            kClasses[cl.kind].fn<<<cl.grid, kClasses[cl.kind].threads, cl.smem, st>>>(a, cl.nmax);
+        }
+        CUADMM_CUDA(cudaGetLastError());
+        ++launches;
+        if (i > 0) {
+            CUADMM_CUDA(cudaEventRecord(side_events[i - 1], st));
+            CUADMM_CUDA(cudaStreamWaitEvent(stream, side_events[i - 1], 0));
+        }
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int cuadmm_plan_create(const int32_t* blk, int64_t nblk, int device, cuadmm_plan** out) {
+    return guarded([&] {
+        CUADMM_REQUIRE(out != nullptr, "out is null");
+        CUADMM_REQUIRE(blk != nullptr || nblk == 0, "blk is null");
+        *out = nullptr;
+        std::unique_ptr<cuadmm_plan> p(new cuadmm_plan());
+        p->layout.init(blk, nblk);
+        if (device >= 0) {
+            int cnt = 0;
+            cudaError_t e = cudaGetDeviceCount(&cnt);
+            if (e != cudaSuccess || cnt == 0) {
+                cudaGetLastError();
+                throw Error(CUADMM_ENODEVICE, "no CUDA device available (pass device=-1 for a host-only plan; compute has no CPU fallback)");
+            }
+            CUADMM_REQUIRE(device < cnt, "device index out of range");
+        }
+        p->device = device;
+        p->build_device();
+        *out = p.release();
+    });
+}
+
+void cuadmm_plan_destroy(cuadmm_plan* plan) { delete plan; }
+int64_t cuadmm_plan_vec_len(const cuadmm_plan* plan) { return plan ? plan->layout.vec_len : -1; }
+int64_t cuadmm_plan_nblk(const cuadmm_plan* plan) { return plan ? (int64_t)plan->layout.blk.size() : -1; }
+int64_t cuadmm_plan_num_sizes(const cuadmm_plan* plan) { return plan ? (int64_t)plan->layout.sizes.size() : -1; }
+
+int cuadmm_plan_sizes(const cuadmm_plan* plan, int32_t* sizes, int32_t* nums, int32_t* is_large) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan, "plan is null");
+        for (size_t i = 0; i < plan->layout.sizes.size(); ++i) {
+            if (sizes) sizes[i] = plan->layout.sizes[i];
+            if (nums) nums[i] = plan->layout.nums[i];
+            if (is_large) is_large[i] = plan->layout.large[i];
+        }
+    });
+}
+
+int cuadmm_plan_totals(const cuadmm_plan* plan, int64_t out[6]) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan && out, "null argument");
+        const BlockLayout& l = plan->layout;
+        out[0] = l.large_mat_num; out[1] = l.sum_large_mat_size; out[2] = l.total_large_mat_size;
+        out[3] = l.small_mat_num; out[4] = l.sum_small_mat_size; out[5] = l.total_small_mat_size;
+    });
+}
+
+int64_t cuadmm_plan_start_indices(const cuadmm_plan* plan, int which, int64_t* out) {
+    if (!plan) return -1;
+    const BlockLayout& l = plan->layout;
+    const std::vector<int64_t>* v = nullptr;
+    switch (which) {
+        case 0: v = &l.large_mat_start; break;
+        case 1: v = &l.large_W_start; break;
+        case 2: v = &l.small_mat_start; break;
+        case 3: v = &l.small_W_start; break;
+        default: return -1;
+    }
+    if (out) std::copy(v->begin(), v->end(), out);
+    return (int64_t)v->size();
+}
+
+int cuadmm_plan_maps(const cuadmm_plan* plan, int32_t* map_B, int32_t* map_M1, int32_t* map_M2) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan && map_B && map_M1 && map_M2, "null argument");
+        plan->layout.maps(map_B, map_M1, map_M2);
+    });
+}
+
+int cuadmm_plan_partition(const cuadmm_plan* plan, int nparts, int32_t* owner, double* part_cost) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan && owner, "null argument");
+        plan->layout.partition(nparts, owner, part_cost);
+    });
+}
+
+int cuadmm_plan_set_jacobi(cuadmm_plan* plan, double threshold, int max_sweeps) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan, "plan is null");
+        CUADMM_REQUIRE(threshold > 0 && max_sweeps > 0, "threshold and max_sweeps must be positive");
+        plan->threshold = threshold;
+        plan->max_sweeps = max_sweeps;
+    });
+}
+
+double cuadmm_plan_last_ms(const cuadmm_plan* plan) { return plan ? plan->last_ms : -1.0; }
+int64_t cuadmm_plan_last_launches(const cuadmm_plan* plan) { return plan ? plan->last_launches : -1; }
+
+int cuadmm_project_psd(cuadmm_plan* plan, const double* d_Xb, double* d_Xproj, void* stream) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan && d_Xb && d_Xproj, "null argument");
+        DeviceGuard g(plan->device);
+        plan->last_launches = plan->project(d_Xb, d_Xproj, (cudaStream_t)stream, nullptr, false);
+    });
+}
+
+static void project_host_impl(cuadmm_plan* plan, const double* h_Xb, double* h_Xproj,
+                              double* h_eig, int32_t* h_sweeps) {
+    CUADMM_REQUIRE(plan && h_Xb && h_Xproj, "null argument");
+    if (plan->device < 0) throw Error(CUADMM_ENODEVICE, "plan was built without a CUDA device; there is no CPU fallback");
+    DeviceGuard g(plan->device);
+    const int64_t L = plan->layout.vec_len;
+    if (plan->d_in.n != L) { plan->d_in.alloc(L); plan->d_out.alloc(L); }
+    plan->d_in.upload(h_Xb, L);
+    CUADMM_CUDA(cudaEventRecord(plan->ev0, 0));
+    plan->last_launches = plan->project(plan->d_in.p, plan->d_out.p, 0, nullptr, h_eig || h_sweeps);
+    CUADMM_CUDA(cudaEventRecord(plan->ev1, 0));
+    plan->d_out.download(h_Xproj, L);
+    if (h_eig) plan->d_eig.download(h_eig, plan->layout.sum_large_mat_size + plan->layout.sum_small_mat_size);
+    if (h_sweeps) plan->d_sweeps.download(h_sweeps, (int64_t)plan->layout.blk.size());
+    CUADMM_CUDA(cudaStreamSynchronize(0));
+    float ms = 0.f;
+    CUADMM_CUDA(cudaEventElapsedTime(&ms, plan->ev0, plan->ev1));
+    plan->last_ms = ms;
+    if (h_eig) {
+        // ascending per block, like dsyevd / Xsyevd / syevj(sort=1)
+        int64_t o = 0;
+        for (size_t k = 0; k < plan->layout.blk.size(); ++k) {
+            std::sort(h_eig + o, h_eig + o + plan->layout.blk[k]);
+            o += plan->layout.blk[k];
+        }
+    }
+}
+
+int cuadmm_project_psd_host(cuadmm_plan* plan, const double* h_Xb, double* h_Xproj) {
+    return guarded([&] { project_host_impl(plan, h_Xb, h_Xproj, nullptr, nullptr); });
+}
+
+int cuadmm_project_psd_eig_host(cuadmm_plan* plan, const double* h_Xb, double* h_Xproj,
+                                double* h_eigvals, int32_t* h_sweeps) {
+    return guarded([&] { project_host_impl(plan, h_Xb, h_Xproj, h_eigvals, h_sweeps); });
+}
+
+int cuadmm_svec_to_smat(cuadmm_plan* plan, const double* d_svec, double* d_large_mat, double* d_small_mat, void* stream) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan && d_svec, "null argument");
+        if (plan->device < 0) throw Error(CUADMM_ENODEVICE, "host-only plan");
+        DeviceGuard g(plan->device);
+        const int nblk = (int)plan->layout.blk.size();
+        if (nblk == 0) return;
+        int nmax = *std::max_element(plan->layout.blk.begin(), plan->layout.blk.end());
+        dim3 grid(nblk, std::min(std::max(nmax / 32, 1), 64));
+        svec_to_smat_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_svec, d_large_mat, d_small_mat,
+            plan->d_blk.p, plan->d_svec_off.p, plan->d_mat_off.p, plan->d_pool.p);
+        CUADMM_CUDA(cudaGetLastError());
+    });
+}
+
+int cuadmm_smat_to_svec(cuadmm_plan* plan, const double* d_large_mat, const double* d_small_mat, double* d_svec, void* stream) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan && d_svec, "null argument");
+        if (plan->device < 0) throw Error(CUADMM_ENODEVICE, "host-only plan");
+        DeviceGuard g(plan->device);
+        const int nblk = (int)plan->layout.blk.size();
+        if (nblk == 0) return;
+        int nmax = *std::max_element(plan->layout.blk.begin(), plan->layout.blk.end());
+        dim3 grid(nblk, std::min(std::max(nmax / 32, 1), 64));
+        smat_to_svec_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_large_mat, d_small_mat, d_svec,
+            plan->d_blk.p, plan->d_svec_off.p, plan->d_mat_off.p, plan->d_pool.p);
+        CUADMM_CUDA(cudaGetLastError());
+    });
+}
+
+}  // extern "C"
