@@ -4,6 +4,7 @@
 #include "plan.h"
 #include <algorithm>
 #include <numeric>
+#include <stdlib.h>
 
 namespace cuadmm {
 
@@ -31,10 +32,65 @@ __device__ __forceinline__ double mat_sum(double v, double* red, int tid) {
     return t;
 }
 
+// max over the NT threads working on one matrix
+template <int NT, bool WARP>
+__device__ __forceinline__ double mat_max(double v, double* red, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (WARP) return v;
+    const int wid = tid >> 5;
+    __syncthreads();
+    if ((tid & 31) == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < NT / 32; ++i) t = fmax(t, red[i]);
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------
 // shared-memory kernel: T threads per CTA, L lanes per column pair, up to RPL rows per lane.
 // WARP = true: one warp per matrix, T/32 matrices per CTA.
+//
+// Instruction budget per column pair is what bounds this kernel (measured: issue-bound, not
+// latency-bound), so: (1) only gamma = g_p.g_q is reduced across the group, the squared column
+// norms alpha/beta are tracked in shared memory by the exact update
+//     alpha' = c^2 alpha - 2cs gamma + s^2 beta,  beta' = s^2 alpha + 2cs gamma + c^2 beta
+// and refreshed from the data at the start of every sweep; (2) the rotation comes from two rsqrt
+// and no division (jacobi_cs2); (3) L is small so one warp instruction serves 32/L pairs.
+// Column stride ld == L (mod 16) makes the L-row windows of the 16/L consecutive round-robin
+// columns a half-warp touches fall into disjoint banks.
 // ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int jacobi_ld(int n, int L) {
+    if (L >= 16) return n | 1;
+    int ld = n;
+    while ((ld & 15) != (L & 15)) ++ld;
+    return ld;
+}
+__host__ __device__ __forceinline__ size_t jacobi_per_mat(int nmax, int L) {
+    return (size_t)jacobi_ld(nmax, L) * nmax + nmax + (nmax + 2) / 2 + 1 + 34;
+}
+
+// rotation from (alpha, beta, gamma) with two rsqrt: cos(2t) = |d|/h, sin(2t) = sign(d) 2gamma/h,
+// d = beta - alpha, h = hypot(d, 2 gamma); c = sqrt((1+cos 2t)/2), s = sin(2t)/(2c).
+// Also returns the tracked-norm updates.
+__device__ __forceinline__ void jacobi_cs2(double alpha, double beta, double gamma, double& c, double& s,
+                                           double& alpha_new, double& beta_new) {
+    const double d = beta - alpha;
+    const double g2 = gamma + gamma;
+    const double rh = rsqrt(fma(d, d, g2 * g2));
+    const double c2 = fabs(d) * rh;                       // cos 2theta in [0,1]
+    const double s2 = (d < 0.0 ? -g2 : g2) * rh;          // sin 2theta
+    const double cc = fma(0.5, c2, 0.5);                  // c^2 in [0.5,1]
+    const double rc = rsqrt(cc);
+    c = cc * rc;
+    s = 0.5 * s2 * rc;
+    const double ss = 1.0 - cc;                           // s^2
+    const double x = s2 * gamma;                          // 2 c s gamma
+    alpha_new = fma(cc, alpha, fma(ss, beta, -x));
+    beta_new = fma(ss, alpha, fma(cc, beta, x));
+}
+
 template <int T, int L, int RPL, bool WARP>
 __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     extern __shared__ double smem[];
@@ -46,36 +102,47 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     const int bi = blockIdx.x * MPC + mat_in_cta;
     if (bi >= a.nblk) return;
 
-    const int ldm = nmax | 1;
-    const size_t per_mat = (size_t)ldm * nmax + nmax + (nmax + 2) / 2 + 1 + 34;
+    const size_t per_mat = jacobi_per_mat(nmax, L);
     double* G = smem + per_mat * mat_in_cta;
-    double* w = G + (size_t)ldm * nmax;
+    double* w = G + (size_t)jacobi_ld(nmax, L) * nmax;     // tracked squared norms, later rebuild weights
     int* pos = (int*)(w + nmax);
     double* red = w + nmax + (nmax + 2) / 2 + 1;
 
     const BlkDesc d = a.desc[bi];
     const int n = d.n;
-    const int ld = n | 1;
+    const int ld = jacobi_ld(n, L);
     const int ntri = n * (n + 1) / 2;
     const double* __restrict__ xin = a.Xb + d.svec_off;
     double* __restrict__ xout = a.Xproj + d.svec_off;
 
-    // ---- svec -> smat (vector_to_matrices), Frobenius norm on the fly ----
-    double f2 = 0.0;
+    // ---- svec -> smat (vector_to_matrices); max |entry| for an exact power-of-two prescale ----
+    double amax = 0.0;
     for (int idx = tid; idx < ntri; idx += NT) {
         int r, c;
         tri_unrank(idx, r, c);
         const double v = xin[idx];
-        f2 += v * v;
+        amax = fmax(amax, fabs(v));          // fmax drops NaN; caught below through the norm
         const double v2 = (r == c) ? v : v * CUADMM_SQRT2INV;
         G[r + c * ld] = v2;
         G[c + r * ld] = v2;
     }
+    amax = mat_max<NT, WARP>(amax, red, tid);
+    int ex = 0;
+    if (amax > 0.0 && amax < 1.7e308) frexp(amax, &ex);
+    mat_sync<WARP>();
+    // Frobenius norm of the 2^-ex prescaled block (no over/underflow for any finite input)
+    double f2 = 0.0;
+    for (int e = tid; e < n * n; e += NT) {
+        const int c = e / n, r = e - c * n;
+        const double v = ldexp(G[r + c * ld], -ex);
+        G[r + c * ld] = v;
+        f2 = fma(v, v, f2);
+    }
     f2 = mat_sum<NT, WARP>(f2, red, tid);
-    const double s = sqrt(f2);
-    if (!(s >= 1e-290)) {
-        // zero block (or NaN input): Pi_+(0) = 0; NaN propagates
-        const double fill = (s == s) ? 0.0 : s;
+    const double sp = sqrt(f2);              // ||A||_F * 2^-ex
+    if (!(sp > 0.0) || !(sp < 1.7e308)) {
+        // zero block: Pi_+(0) = 0; NaN/Inf input propagates NaN
+        const double fill = (sp == 0.0) ? 0.0 : (sp - sp);
         for (int idx = tid; idx < ntri; idx += NT) {
             xout[idx] = fill;
             if (a.epi.X) {
@@ -86,15 +153,12 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
                 a.epi.SmC[gi] = Sv - a.epi.Cd[gi];
             }
         }
-        if (tid == 0) {
-            if (a.sweeps_out) a.sweeps_out[d.index] = 0;
-        }
+        if (tid == 0 && a.sweeps_out) a.sweeps_out[d.index] = 0;
         if (a.eig_out) for (int j = tid; j < n; j += NT) a.eig_out[d.w_off + j] = fill;
         return;
     }
-    const double inv_s = 1.0 / s;
-    mat_sync<WARP>();
-    // G <- A / s + I
+    const double inv_s = 1.0 / sp;
+    // G <- A / ||A||_F + I
     for (int e = tid; e < n * n; e += NT) {
         const int c = e / n, r = e - c * n;
         const double v = G[r + c * ld] * inv_s;
@@ -108,8 +172,19 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     const int grp = tid / L, lane = tid % L;
     const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << ((tid & 31) / L * L));
     const double thr2 = a.threshold * a.threshold;
+    const double tiny2 = 1.2325951644078309e-32;  // 2^-106: rotations below rounding level are skipped
     int sweeps = 0;
     while (sweeps < a.max_sweeps) {
+        // refresh the tracked squared norms from the data
+        for (int j = grp; j < n; j += NG) {
+            const double* Gj = G + j * ld;
+            double al = 0.0;
+            for (int r = lane; r < n; r += L) al = fma(Gj[r], Gj[r], al);
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) al += __shfl_xor_sync(gmask, al, o);
+            if (lane == 0) w[j] = al;
+        }
+        mat_sync<WARP>();
         int big = 0;
         for (int step = 0; step < m - 1; ++step) {
             for (int k = grp; k < half; k += NG) {
@@ -120,37 +195,35 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
                 double* __restrict__ Gp = G + p * ld;
                 double* __restrict__ Gq = G + q * ld;
                 double gp[RPL], gq[RPL];
-                double al = 0.0, be = 0.0, ga = 0.0;
+                double ga = 0.0;
 #pragma unroll
                 for (int i = 0; i < RPL; ++i) {
                     const int r = lane + i * L;
                     if (r < n) {
                         gp[i] = Gp[r];
                         gq[i] = Gq[r];
-                        al = fma(gp[i], gp[i], al);
-                        be = fma(gq[i], gq[i], be);
                         ga = fma(gp[i], gq[i], ga);
                     } else {
                         gp[i] = 0.0; gq[i] = 0.0;
                     }
                 }
+                const double al = w[p], be = w[q];
 #pragma unroll
-                for (int o = L / 2; o > 0; o >>= 1) {
-                    al += __shfl_xor_sync(gmask, al, o);
-                    be += __shfl_xor_sync(gmask, be, o);
-                    ga += __shfl_xor_sync(gmask, ga, o);
-                }
-                if (ga * ga > thr2 * al * be) big = 1;
-                double c, sn;
-                if (jacobi_cs(al, be, ga, c, sn)) {
+                for (int o = L / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(gmask, ga, o);
+                const double g2 = ga * ga, ab = al * be;
+                if (g2 > thr2 * ab) big = 1;
+                if (g2 > tiny2 * ab) {
+                    double c, sn, an, bn;
+                    jacobi_cs2(al, be, ga, c, sn, an, bn);
 #pragma unroll
                     for (int i = 0; i < RPL; ++i) {
                         const int r = lane + i * L;
                         if (r < n) {
-                            Gp[r] = c * gp[i] - sn * gq[i];
-                            Gq[r] = sn * gp[i] + c * gq[i];
+                            Gp[r] = fma(c, gp[i], -sn * gq[i]);
+                            Gq[r] = fma(sn, gp[i], c * gq[i]);
                         }
                     }
+                    if (lane == 0) { w[p] = an; w[q] = bn; }
                 }
             }
             mat_sync<WARP>();
@@ -161,6 +234,7 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     }
 
     // ---- eigenvalues from the column norms; weights of the positive part ----
+    const double s_true = ldexp(sp, ex);     // ||A||_F
     for (int j = grp; j < n; j += NG) {
         const double* Gj = G + j * ld;
         double al = 0.0;
@@ -169,10 +243,9 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
         for (int o = L / 2; o > 0; o >>= 1) al += __shfl_xor_sync(gmask, al, o);
         if (lane == 0) {
             const double sigma = sqrt(al);
-            const double lam = s * (sigma - 1.0);
-            // sqrt of the rebuild weight: Pi_+ = sum_j w_j g_j g_j^T, w_j = lam_j / sigma_j^2
-            w[j] = (sigma > 1.0) ? sqrt(lam / al) : 0.0;
-            if (a.eig_out) a.eig_out[d.w_off + j] = lam;
+            // sqrt of the rebuild weight: Pi_+ = s sum_j (sigma_j - 1)/sigma_j^2 g_j g_j^T
+            w[j] = (sigma > 1.0) ? sqrt((sigma - 1.0) / al) : 0.0;
+            if (a.eig_out) a.eig_out[d.w_off + j] = s_true * (sigma - 1.0);
         }
     }
     mat_sync<WARP>();
@@ -203,6 +276,7 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
             const double* Gj = G + pos[jj] * ld;
             acc = fma(Gj[r], Gj[c], acc);
         }
+        acc *= s_true;
         const double out = (r == c) ? acc : acc * CUADMM_SQRT2;
         xout[idx] = out;
         if (a.epi.X) {
@@ -402,30 +476,65 @@ __global__ void smat_to_svec_kernel(const double* __restrict__ large_mat, const 
 }
 
 // ------------------------------------------------------------------------------------------
-// size classes
+// kernel variants and size classes
 // ------------------------------------------------------------------------------------------
-struct KernelClass {
-    int nmax_allowed;
+struct Variant {
+    int nmax_allowed;   // L * RPL rows, and the shared-memory limit
     int threads;
+    int L;
     int mats_per_cta;
     void (*fn)(ProjArgs, int);
 };
 
-static const KernelClass kClasses[] = {
-    {16, 128, 4, proj_jacobi_kernel<128, 4, 4, true>},
-    {32, 128, 1, proj_jacobi_kernel<128, 8, 4, false>},
-    {64, 512, 1, proj_jacobi_kernel<512, 16, 4, false>},
-    {96, 768, 1, proj_jacobi_kernel<768, 16, 6, false>},
-    {128, 1024, 1, proj_jacobi_kernel<1024, 16, 8, false>},
-    {168, 672, 1, proj_jacobi_kernel<672, 16, 11, false>},
+#define CUADMM_VARIANT(T, L, RPL, WARP) {((L) * (RPL) > 168 ? 168 : (L) * (RPL)), T, L, (WARP) ? (T) / 32 : 1, proj_jacobi_kernel<T, L, RPL, WARP>}
+static const Variant kVariants[] = {
+    /* 0*/ CUADMM_VARIANT(128, 4, 4, true),
+    /* 1*/ CUADMM_VARIANT(64, 4, 8, false),
+    /* 2*/ CUADMM_VARIANT(128, 8, 4, false),
+    /* 3*/ CUADMM_VARIANT(128, 4, 16, false),
+    /* 4*/ CUADMM_VARIANT(256, 8, 8, false),
+    /* 5*/ CUADMM_VARIANT(512, 16, 4, false),
+    /* 6*/ CUADMM_VARIANT(384, 8, 12, false),
+    /* 7*/ CUADMM_VARIANT(768, 16, 6, false),
+    /* 8*/ CUADMM_VARIANT(512, 8, 16, false),
+    /* 9*/ CUADMM_VARIANT(1024, 16, 8, false),
+    /*10*/ CUADMM_VARIANT(672, 16, 11, false),
+    /*11*/ CUADMM_VARIANT(192, 4, 24, false),
+    /*12*/ CUADMM_VARIANT(256, 4, 32, false),
+    /*13*/ CUADMM_VARIANT(352, 8, 21, false),
+    /*14*/ CUADMM_VARIANT(256, 8, 4, true),
+    /*15*/ CUADMM_VARIANT(128, 8, 8, false),
 };
-static const int kNumSmemClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
-static const int kGlobalKind = kNumSmemClasses;
+static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+static const int kGlobalKind = -1;
 
-static size_t smem_bytes(int nmax, int mats_per_cta) {
-    const size_t ldm = (size_t)(nmax | 1);
-    const size_t per_mat = ldm * nmax + nmax + (nmax + 2) / 2 + 1 + 34;
-    return per_mat * sizeof(double) * mats_per_cta;
+// size class = (largest n, variant).  Default table from the tuning sweep in
+// profiles/jacobi_tuning_r01.md; CUADMM_JACOBI_CLASSES="16:0,32:1,..." overrides it (tuning only).
+struct SizeClass { int nmax; int variant; };
+static std::vector<SizeClass> size_classes() {
+    std::vector<SizeClass> t = {{16, 0}, {32, 1}, {64, 3}, {96, 11}, {128, 8}, {168, 13}};
+    const char* env = getenv("CUADMM_JACOBI_CLASSES");
+    if (env && *env) {
+        std::vector<SizeClass> u;
+        const char* q = env;
+        while (*q) {
+            char* end = nullptr;
+            long nm = strtol(q, &end, 10);
+            if (end == q || *end != ':') break;
+            q = end + 1;
+            long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v >= 0 && v < kNumVariants && nm >= 1 && nm <= kVariants[v].nmax_allowed) u.push_back({(int)nm, (int)v});
+            q = (*end == ',') ? end + 1 : end;
+            if (*end != ',') break;
+        }
+        if (!u.empty()) t = u;
+    }
+    return t;
+}
+
+static size_t smem_bytes(int nmax, const Variant& v) {
+    return jacobi_per_mat(nmax, v.L) * sizeof(double) * v.mats_per_cta;
 }
 
 }  // namespace cuadmm
@@ -450,31 +559,33 @@ void cuadmm_plan::build_device() {
     for (int64_t k = 0; k < nblk; ++k) w_off[k + 1] = w_off[k] + layout.blk[k];
 
     // classify
-    std::vector<std::vector<int64_t>> members(kNumSmemClasses + 1);
+    const std::vector<SizeClass> table = size_classes();
+    std::vector<std::vector<int64_t>> members(table.size() + 1);
     for (int64_t k = 0; k < nblk; ++k) {
         const int n = layout.blk[k];
-        int kind = kGlobalKind;
-        for (int c = 0; c < kNumSmemClasses; ++c) if (n <= kClasses[c].nmax_allowed) { kind = c; break; }
-        members[kind].push_back(k);
+        size_t ci = table.size();
+        for (size_t c = 0; c < table.size(); ++c) if (n <= table[c].nmax) { ci = c; break; }
+        members[ci].push_back(k);
     }
     h_desc.clear(); classes.clear();
     int64_t scratch = 0;
     // heaviest classes first so their launches start first
-    for (int kind = kNumSmemClasses; kind >= 0; --kind) {
-        auto& mem = members[kind];
+    for (int ci = (int)table.size(); ci >= 0; --ci) {
+        auto& mem = members[ci];
         if (mem.empty()) continue;
         std::stable_sort(mem.begin(), mem.end(), [&](int64_t a, int64_t b) { return layout.blk[a] > layout.blk[b]; });
         Class cl;
-        cl.kind = kind;
+        cl.kind = (ci == (int)table.size()) ? kGlobalKind : table[ci].variant;
         cl.nmax = layout.blk[mem[0]];
         cl.count = (int32_t)mem.size();
         cl.first = (int64_t)h_desc.size();
-        if (kind == kGlobalKind) {
+        if (cl.kind == kGlobalKind) {
             cl.smem = 0;
             cl.grid = cl.count;
         } else {
-            cl.smem = smem_bytes(cl.nmax, kClasses[kind].mats_per_cta);
-            cl.grid = (cl.count + kClasses[kind].mats_per_cta - 1) / kClasses[kind].mats_per_cta;
+            const Variant& v = kVariants[cl.kind];
+            cl.smem = smem_bytes(cl.nmax, v);
+            cl.grid = (cl.count + v.mats_per_cta - 1) / v.mats_per_cta;
         }
         for (int64_t k : mem) {
             BlkDesc d;
@@ -483,7 +594,7 @@ void cuadmm_plan::build_device() {
             d.n = layout.blk[k];
             d.index = (int32_t)k;
             d.scratch_off = 0;
-            if (kind == kGlobalKind) {
+            if (cl.kind == kGlobalKind) {
                 d.scratch_off = scratch;
                 const int64_t n = d.n;
                 scratch += n * n + n + (n + 2) / 2 + 1;
@@ -512,9 +623,10 @@ void cuadmm_plan::build_device() {
         CUADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         side_streams.push_back(s); side_events.push_back(e);
     }
-    for (int c = 0; c < kNumSmemClasses; ++c) {
-        CUADMM_CUDA(cudaFuncSetAttribute((const void*)kClasses[c].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes(kClasses[c].nmax_allowed, kClasses[c].mats_per_cta)));
+    for (const Class& cl : classes) {
+        if (cl.kind == kGlobalKind) continue;
+        CUADMM_CUDA(cudaFuncSetAttribute((const void*)kVariants[cl.kind].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes(kVariants[cl.kind].nmax_allowed, kVariants[cl.kind])));
     }
     CUADMM_CUDA(cudaDeviceSynchronize());
 }
@@ -545,7 +657,7 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
         if (cl.kind == kGlobalKind) {
             proj_jacobi_global_kernel<<<cl.grid, 1024, 0, st>>>(a);
         } else {
-            kClasses[cl.kind].fn<<<cl.grid, kClasses[cl.kind].threads, cl.smem, st>>>(a, cl.nmax);
+            kVariants[cl.kind].fn<<<cl.grid, kVariants[cl.kind].threads, cl.smem, st>>>(a, cl.nmax);
         }
         CUADMM_CUDA(cudaGetLastError());
         ++launches;

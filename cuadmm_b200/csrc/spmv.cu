@@ -1,0 +1,287 @@
+// spmv.cu — hand-written CSR SpMV for the constraint operators A (m x vec_len) and At
+// (vec_len x m), replacing cusparseSpMV(CSR_ALG1) (include/cuadmm/cusparse.h:70-83) and, through
+// the fused epilogues, the axpy / axpby / elementwise launches around each call site in
+// src/solver.cu (478-482, 514-527, 695-699, 721-758, 764-777).
+//
+// Shape of the data: SPOT/moment matrices have ~2-5 non-zeros per constraint row, At has many
+// empty rows and a handful of very long ones (a shared moment entry used by thousands of
+// constraints).  So: G lanes per row (G from the mean row length) for ordinary rows, and one warp
+// per "long" row (> kLongRow non-zeros) appended to the same grid.  HBM-bound: 12 B per non-zero
+// (value + int32 column), coalesced across the lanes of a group.
+#include "spmv.h"
+#include <algorithm>
+
+namespace cuadmm {
+
+static constexpr int kLongRow = 256;
+static constexpr int kThreads = 256;
+
+__device__ __forceinline__ void spmv_store(const SpmvEpilogue& e, double alpha, double beta, double* y,
+                                           int64_t i, double r, double& acc0, double& acc1) {
+    switch (e.mode) {
+        case 0:
+            y[i] = (beta == 0.0) ? alpha * r : alpha * r + beta * y[i];
+            break;
+        case 1: {  // rhsy = Rp / sig - A*SmC
+            const double sig = e.scal[0];
+            y[i] = e.aux1[i] / sig - r;
+            break;
+        }
+        case 2: {  // Rd1 = At*y - C ; Xb = X + sig * Rd1
+            const double sig = e.scal[0];
+            const double rd1 = r - e.aux1[i];
+            y[i] = rd1;
+            e.out2[i] = e.aux2[i] + sig * rd1;
+            break;
+        }
+        case 3: {  // Rd1 = At*y - C ; Rd = Rd1 + S ; X += tau*sig*Rd ; sums |Rd|^2, <C,X>
+            const double sig = e.scal[0], tau = e.scal[1];
+            const double c = e.aux1[i];
+            const double rd = (r - c) + e.aux2[i];
+            y[i] = rd;                                   // Rd
+            const double xn = e.out2[i] + (tau * sig) * rd;
+            e.out2[i] = xn;                              // X
+            acc0 = fma(rd, rd, acc0);
+            acc1 = fma(c, xn, acc1);
+            break;
+        }
+        case 4: {  // Rp = b - A*X ; sums |normA .* Rp|^2 and <b, y>
+            const double b = e.aux1[i];
+            const double rp = b - r;
+            y[i] = rp;
+            const double t = e.aux2[i] * rp;             // normA[i] * Rp[i]  (bscale applied by the caller)
+            acc0 = fma(t, t, acc0);
+            acc1 = fma(b, e.aux3[i], acc1);              // <b, y>
+            break;
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
+        int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+        const double* __restrict__ val, const double* __restrict__ x, double* y, double alpha, double beta,
+        SpmvEpilogue e, const int32_t* __restrict__ long_rows, int n_long, int main_blocks,
+        const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    __shared__ double red[2][kThreads / 32];
+    double acc0 = 0.0, acc1 = 0.0;
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x < main_blocks) {
+        const int sub = threadIdx.x % G;
+        const int64_t gid = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+        const int64_t ngroups = (int64_t)main_blocks * kThreads / G;
+        const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
+        for (int64_t i = gid; i < rows; i += ngroups) {
+            const int p0 = rowptr[i], p1 = rowptr[i + 1];
+            double r = 0.0;
+            if (p1 - p0 <= kLongRow) {
+                for (int p = p0 + sub; p < p1; p += G) r = fma(val[p], x[colind[p]], r);
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) r += __shfl_xor_sync(gmask, r, o);
+            if (sub == 0 && p1 - p0 <= kLongRow) spmv_store(e, alpha, beta, y, i, r, acc0, acc1);
+        }
+    } else {
+        // long rows: one warp per row
+        const int w = ((int)blockIdx.x - main_blocks) * (kThreads / 32) + (threadIdx.x >> 5);
+        const int nw = ((int)gridDim.x - main_blocks) * (kThreads / 32);
+        for (int li = w; li < n_long; li += nw) {
+            const int64_t i = long_rows[li];
+            const int p0 = rowptr[i], p1 = rowptr[i + 1];
+            double r = 0.0;
+            for (int p = p0 + lane; p < p1; p += 32) r = fma(val[p], x[colind[p]], r);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (lane == 0) spmv_store(e, alpha, beta, y, i, r, acc0, acc1);
+        }
+    }
+    if (e.partial) {
+        // deterministic two-stage reduction: fixed tree inside the CTA, fixed order across CTAs later
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        if (lane == 0) { red[0][threadIdx.x >> 5] = acc0; red[1][threadIdx.x >> 5] = acc1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = 0; k < kThreads / 32; ++k) { s0 += red[0][k]; s1 += red[1][k]; }
+            e.partial[2 * blockIdx.x] = s0;
+            e.partial[2 * blockIdx.x + 1] = s1;
+        }
+    }
+}
+
+struct SpmvAux {
+    DevBuf<int32_t> long_rows;
+    int n_long = 0;
+    int main_blocks = 0, long_blocks = 0;
+};
+
+}  // namespace cuadmm
+
+using namespace cuadmm;
+
+// the aux data (long-row list, grid shape) hangs off the handle
+struct cuadmm_spmv_full : cuadmm_spmv_s {
+    SpmvAux aux;
+    const int* done_flag = nullptr;
+};
+
+namespace cuadmm {
+
+int spmv_grid(const cuadmm_spmv_s& A_) {
+    const cuadmm_spmv_full& A = static_cast<const cuadmm_spmv_full&>(A_);
+    return A.aux.main_blocks + A.aux.long_blocks;
+}
+
+void spmv_set_done_flag(cuadmm_spmv_s& A_, const int* flag) {
+    static_cast<cuadmm_spmv_full&>(A_).done_flag = flag;
+}
+
+void spmv_launch(const cuadmm_spmv_s& A_, double alpha, const double* x, double beta, double* y,
+                 const SpmvEpilogue& epi, cudaStream_t stream, int* grid_out) {
+    const cuadmm_spmv_full& A = static_cast<const cuadmm_spmv_full&>(A_);
+    const int grid = A.aux.main_blocks + A.aux.long_blocks;
+    if (grid_out) *grid_out = grid;
+    if (A.rows == 0 || grid == 0) return;
+#define CUADMM_SPMV_CASE(G)                                                                            \
+    case G:                                                                                            \
+        spmv_csr_kernel<G><<<grid, kThreads, 0, stream>>>(A.rows, A.rowptr.p, A.colind.p, A.val.p, x, y, \
+            alpha, beta, epi, A.aux.long_rows.p, A.aux.n_long, A.aux.main_blocks, A.done_flag);         \
+        break;
+    switch (A.group) {
+        CUADMM_SPMV_CASE(1)
+        CUADMM_SPMV_CASE(2)
+        CUADMM_SPMV_CASE(4)
+        CUADMM_SPMV_CASE(8)
+        CUADMM_SPMV_CASE(16)
+        CUADMM_SPMV_CASE(32)
+        default: throw Error(CUADMM_EINVAL, "bad spmv group size");
+    }
+#undef CUADMM_SPMV_CASE
+    CUADMM_CUDA(cudaGetLastError());
+}
+
+cuadmm_spmv_s* spmv_create(int64_t rows, int64_t cols, int64_t nnz, const int32_t* h_rowptr,
+                         const int32_t* h_colind, const double* h_val, int device) {
+    CUADMM_REQUIRE(rows >= 0 && cols >= 0 && nnz >= 0, "negative dimension");
+    CUADMM_REQUIRE(nnz <= INT32_MAX, "nnz exceeds int32 row pointers");
+    CUADMM_REQUIRE(h_rowptr != nullptr, "rowptr is null");
+    CUADMM_REQUIRE(h_rowptr[0] == 0 && h_rowptr[rows] == nnz, "rowptr does not span nnz");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        throw Error(CUADMM_ENODEVICE, "no CUDA device available; SpMV has no CPU fallback");
+    }
+    CUADMM_REQUIRE(device >= 0 && device < cnt, "device index out of range");
+    std::unique_ptr<cuadmm_spmv_full> A(new cuadmm_spmv_full());
+    A->device = device; A->rows = rows; A->cols = cols; A->nnz = nnz;
+    DeviceGuard g(device);
+    A->rowptr.alloc(rows + 1); A->rowptr.upload(h_rowptr, rows + 1);
+    A->colind.alloc(std::max<int64_t>(nnz, 1)); A->colind.upload(h_colind, nnz);
+    A->val.alloc(std::max<int64_t>(nnz, 1)); A->val.upload(h_val, nnz);
+    std::vector<int32_t> longs;
+    int64_t short_nnz = 0, short_rows = 0;
+    for (int64_t i = 0; i < rows; ++i) {
+        CUADMM_REQUIRE(h_rowptr[i + 1] >= h_rowptr[i], "rowptr not monotone");
+        const int len = h_rowptr[i + 1] - h_rowptr[i];
+        if (len > kLongRow) longs.push_back((int32_t)i);
+        else if (len > 0) { short_nnz += len; ++short_rows; }
+    }
+    for (int64_t p = 0; p < nnz; ++p) CUADMM_REQUIRE(h_colind[p] >= 0 && h_colind[p] < cols, "column index out of range");
+    const double mean = short_rows ? (double)short_nnz / (double)short_rows : 1.0;
+    int G = 1;
+    while (G < 32 && (double)G < mean) G <<= 1;   // smallest power of two >= mean row length
+    A->group = G;
+    A->aux.n_long = (int)longs.size();
+    if (!longs.empty()) { A->aux.long_rows.upload(longs); }
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    const int64_t need = (rows * G + kThreads - 1) / kThreads;
+    A->aux.main_blocks = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)sm * 8);
+    A->aux.long_blocks = longs.empty() ? 0 : (int)std::min<int64_t>(((int64_t)longs.size() + 7) / 8, (int64_t)sm);
+    CUADMM_CUDA(cudaStreamSynchronize(0));
+    return A.release();
+}
+
+}  // namespace cuadmm
+
+extern "C" {
+
+int cuadmm_spmv_create(int64_t rows, int64_t cols, int64_t nnz, const int32_t* h_rowptr, const int32_t* h_colind,
+                       const double* h_val, int device, cuadmm_spmv_t** out) {
+    return guarded([&] {
+        CUADMM_REQUIRE(out != nullptr, "out is null");
+        *out = nullptr;
+        *out = spmv_create(rows, cols, nnz, h_rowptr, h_colind, h_val, device);
+    });
+}
+
+void cuadmm_spmv_destroy(cuadmm_spmv_t* A) { delete static_cast<cuadmm_spmv_full*>(A); }
+
+int cuadmm_spmv(cuadmm_spmv_t* A, double alpha, const double* d_x, double beta, double* d_y, void* stream) {
+    return guarded([&] {
+        CUADMM_REQUIRE(A && d_x && d_y, "null argument");
+        DeviceGuard g(A->device);
+        SpmvEpilogue e;
+        spmv_launch(*A, alpha, d_x, beta, d_y, e, (cudaStream_t)stream);
+    });
+}
+
+int cuadmm_spmv_host(cuadmm_spmv_t* A, double alpha, const double* h_x, double beta, double* h_y) {
+    return guarded([&] {
+        CUADMM_REQUIRE(A && h_x && h_y, "null argument");
+        DeviceGuard g(A->device);
+        if (A->d_x.n != A->cols) A->d_x.alloc(A->cols);
+        if (A->d_y.n != A->rows) A->d_y.alloc(A->rows);
+        A->d_x.upload(h_x, A->cols);
+        A->d_y.upload(h_y, A->rows);
+        SpmvEpilogue e;
+        spmv_launch(*A, alpha, A->d_x.p, beta, A->d_y.p, e, 0);
+        A->d_y.download(h_y, A->rows);
+        CUADMM_CUDA(cudaStreamSynchronize(0));
+    });
+}
+
+// get_normA on host arrays (src/kernels/sparse_matrix_norm.cu:11-31): serial sum per constraint,
+// floor 1.0, in-place division.  Init-time; the solver runs the same arithmetic.
+int cuadmm_normA_host(int64_t con_num, const int32_t* At_col_ptrs, double* At_vals, double* normA) {
+    return guarded([&] {
+        CUADMM_REQUIRE(At_col_ptrs && At_vals && normA, "null argument");
+        for (int64_t i = 0; i < con_num; ++i) {
+            double norm = 0.0;
+            for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) norm += At_vals[p] * At_vals[p];
+            norm = std::max(1.0, sqrt(norm));
+            normA[i] = norm;
+            for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) At_vals[p] /= norm;
+        }
+    });
+}
+
+// CSC -> CSR of the same matrix (cusparseCsr2cscEx2 in the reference, include/cuadmm/cusparse.h:35-49):
+// counting sort, row-major output with ascending column ids inside a row.
+int cuadmm_csc_to_csr_host(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t* col_ptrs, const int32_t* row_ids,
+                           const double* vals, int32_t* row_ptrs, int32_t* col_ids, double* out_vals) {
+    return guarded([&] {
+        CUADMM_REQUIRE(col_ptrs && row_ptrs, "null argument");
+        std::vector<int64_t> cnt(nrows + 1, 0);
+        for (int64_t p = 0; p < nnz; ++p) {
+            CUADMM_REQUIRE(row_ids[p] >= 0 && row_ids[p] < nrows, "row index out of range");
+            cnt[row_ids[p] + 1]++;
+        }
+        for (int64_t i = 0; i < nrows; ++i) cnt[i + 1] += cnt[i];
+        for (int64_t i = 0; i <= nrows; ++i) row_ptrs[i] = (int32_t)cnt[i];
+        std::vector<int64_t> next(cnt.begin(), cnt.end() - 1);
+        for (int64_t c = 0; c < ncols; ++c)
+            for (int p = col_ptrs[c]; p < col_ptrs[c + 1]; ++p) {
+                const int64_t q = next[row_ids[p]]++;
+                col_ids[q] = (int32_t)c;
+                out_vals[q] = vals[p];
+            }
+    });
+}
+
+}  // extern "C"

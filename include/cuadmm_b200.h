@@ -104,7 +104,7 @@ int cuadmm_plan_set_jacobi(cuadmm_plan* plan, double threshold, int max_sweeps);
  * cuadmm_normA replaces get_normA (src/kernels/sparse_matrix_norm.cu:11-44).
  * cuadmm_csc_to_csr replaces CSC_to_CSR_cusparse (include/cuadmm/cusparse.h:35-49).
  * -------------------------------------------------------------------------- */
-typedef struct cuadmm_spmv cuadmm_spmv_t;
+typedef struct cuadmm_spmv_s cuadmm_spmv_t;
 
 int  cuadmm_spmv_create(int64_t rows, int64_t cols, int64_t nnz,
                         const int32_t* h_rowptr, const int32_t* h_colind, const double* h_val,
@@ -126,7 +126,7 @@ int  cuadmm_csc_to_csr_host(int64_t nrows, int64_t ncols, int64_t nnz,
  * A is given as the CSC arrays of At (vec_len x m) == CSR arrays of A (m x vec_len),
  * exactly what SDPSolver::init hands to get_A (src/solver.cu:91-95).
  * -------------------------------------------------------------------------- */
-typedef struct cuadmm_ysolve cuadmm_ysolve_t;
+typedef struct cuadmm_ysolve_s cuadmm_ysolve_t;
 
 int  cuadmm_ysolve_create(int64_t m, int64_t vec_len, int64_t nnz,
                           const int32_t* h_A_rowptr, const int32_t* h_A_colind, const double* h_A_val,
