@@ -35,6 +35,7 @@ struct cuadmm_plan {
     std::vector<cudaStream_t> side_streams;    // classes run concurrently on these
     std::vector<cudaEvent_t> side_events;
     cudaEvent_t fork_event = nullptr;
+    const int* done_flag = nullptr;            // device stop flag honoured by the kernels (solver)
     double last_ms = 0.0;
     int64_t last_launches = 0;
 

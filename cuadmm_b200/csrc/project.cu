@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     const int mat_in_cta = WARP ? (threadIdx.x >> 5) : 0;
     const int bi = blockIdx.x * MPC + mat_in_cta;
     if (bi >= a.nblk) return;
+    if (a.done_flag && *a.done_flag) return;
 
     const size_t per_mat = jacobi_per_mat(nmax, L);
     double* G = smem + per_mat * mat_in_cta;
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(1024) proj_jacobi_global_kernel(ProjArgs a) {
     const int tid = threadIdx.x;
     const int bi = blockIdx.x;
     if (bi >= a.nblk) return;
+    if (a.done_flag && *a.done_flag) return;
     const BlkDesc d = a.desc[bi];
     const int n = d.n;
     const int64_t ld = n;
@@ -653,6 +655,7 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
         a.eig_out = want_eig ? d_eig.p : nullptr;
         a.sweeps_out = want_eig ? d_sweeps.p : nullptr;
         a.scratch = d_scratch.p;
+        a.done_flag = done_flag;
         if (epi) a.epi = *epi; else { a.epi.X = nullptr; a.epi.Rd1 = nullptr; a.epi.Cd = nullptr; a.epi.S = nullptr; a.epi.SmC = nullptr; a.epi.sig_ptr = nullptr; }
         if (cl.kind == kGlobalKind) {
             proj_jacobi_global_kernel<<<cl.grid, 1024, 0, st>>>(a);

@@ -63,6 +63,7 @@ struct ProjArgs {
     double* eig_out;        // optional (null): eigenvalues, unsorted, at desc.w_off
     int32_t* sweeps_out;    // optional (null): sweeps used, at desc.index
     double* scratch;        // global variant
+    const int* done_flag;   // optional device flag: kernels return at once when *done_flag != 0
     ProjEpilogue epi;
 };
 

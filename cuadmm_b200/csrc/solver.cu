@@ -1,0 +1,612 @@
+// solver.cu — the sGS-ADMM iteration of the reference (SDPSolver::init / solve, src/solver.cu:27-822)
+// on top of the device-resident hot path.  One iteration =
+//   K1  rhsy = Rp/sig - A (S-C)                  SpMV(A)  + fused axpy            (:478-482)
+//   K2  y = (A A^T)^-1 rhsy                      device triangular sweeps          (:487-500)
+//   K3  Rd1 = A^T y - C ; Xb = X + sig Rd1       SpMV(At) + fused axpby/axpy       (:514-527)
+//   K4  Xproj = Pi+(Xb) ; S ; SmC                fused Jacobi projection           (:531-675)
+//   K5-K6 (sGS only) second rhsy / y             (:693-717)
+//   K7  Rd = A^T y - C + S ; X += tau sig Rd     SpMV(At) + fused update + |Rd|^2, <C,X>   (:721-758)
+//   K8  Rp = b - A X ; |normA Rp|^2 ; <b,y>      SpMV(A)  + fused reductions       (:764-777)
+//   K9  residuals, sigma rule, history, stop     one tiny kernel, no host sync     (:772-810)
+// The host only enqueues; it reads the state back when a log line is due (every 50/100 iterations,
+// like the reference's printout) and finds out there whether the device-side stop test fired.
+#include "solver.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <string>
+#include <string.h>
+#include <stdlib.h>
+
+namespace cuadmm {
+
+void spmv_set_done_flag(cuadmm_spmv_s& A, const int* flag);
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+static constexpr int kEwThreads = 256;
+
+// ADMM branch of step 4 (no second y-solve): Rd = Rd1 + S ; X += tau*sig*Rd ; partial sums
+__global__ void __launch_bounds__(kEwThreads) x_update_kernel(int64_t n, const double* __restrict__ Rd1,
+        const double* __restrict__ S, const double* __restrict__ Cd, double* Rd, double* X,
+        const DevState* st, double* partial) {
+    if (st->done) return;
+    __shared__ double red[2][kEwThreads / 32];
+    const double ts = st->tau * st->sig;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kEwThreads) {
+        const double rd = Rd1[i] + S[i];
+        Rd[i] = rd;
+        const double xn = X[i] + ts * rd;
+        X[i] = xn;
+        a0 = fma(rd, rd, a0);
+        a1 = fma(Cd[i], xn, a1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < kEwThreads / 32; ++k) { s0 += red[0][k]; s1 += red[1][k]; }
+        partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1;
+    }
+}
+
+// K9: fixed-order reduction of the per-CTA partials, then the reference's scalar logic
+__global__ void __launch_bounds__(256) scalar_update_kernel(DevState* st, const double* __restrict__ part_rd, int n_rd,
+        const double* __restrict__ part_rp, int n_rp, double* hist, int64_t hist_cap) {
+    if (st->done) return;
+    __shared__ double sm[4][256];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n_rd; i += 256) { v[0] += part_rd[2 * i]; v[1] += part_rd[2 * i + 1]; }
+    for (int i = threadIdx.x; i < n_rp; i += 256) { v[2] += part_rp[2 * i]; v[3] += part_rp[2 * i + 1]; }
+    for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] = v[q];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] += sm[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const double sumRd = sm[0][0], sumCX = sm[1][0], sumRp = sm[2][0], sumby = sm[3][0];
+    const int iter = st->iter;
+    const double errRp = st->bscale * sqrt(sumRp) / st->norm_borg;
+    const double pobj = sumCX * st->objscale;
+    const double errRd = st->Cscale * sqrt(sumRd) / st->norm_Corg;
+    const double dobj = sumby * st->objscale;
+    const double maxfeas = fmax(errRp, errRd);
+    const double relgap = fabs(pobj - dobj) / (1 + fabs(pobj) + fabs(dobj));
+    const double feasratio = st->ratioconst * errRp / errRd;
+    if (feasratio < 1) st->prim_win += 1; else st->dual_win += 1;
+    double sig = st->sig;
+    if (((iter <= st->sig_update_threshold) && ((iter % st->sig_update_stage_1) == 1)) ||
+        ((iter > st->sig_update_threshold) && ((iter % st->sig_update_stage_2) == 1))) {
+        if (st->prim_win > 1.2 * st->dual_win) {
+            st->prim_win = 0;
+            sig = fmin(st->sigmax, sig * st->sigscale);
+        } else if (st->dual_win > 1.2 * st->prim_win) {
+            st->dual_win = 0;
+            sig = fmax(st->sigmin, sig / st->sigscale);
+        }
+    }
+    st->sig = sig;
+    st->errRp = errRp; st->errRd = errRd; st->pobj = pobj; st->dobj = dobj;
+    st->maxfeas = maxfeas; st->relgap = relgap; st->feasratio = feasratio;
+    if (iter - 1 < hist_cap) {
+        const int64_t k = iter - 1;
+        hist[0 * hist_cap + k] = pobj;  hist[1 * hist_cap + k] = dobj;
+        hist[2 * hist_cap + k] = errRp; hist[3 * hist_cap + k] = errRd;
+        hist[4 * hist_cap + k] = relgap; hist[5 * hist_cap + k] = sig;
+        hist[6 * hist_cap + k] = st->bscale; hist[7 * hist_cap + k] = st->Cscale;
+    }
+    const int next = iter + 1;
+    st->iter = next;
+    double tau = (next < st->switch_admm) ? 1.95 : 1.618;
+    if (errRd < st->stop_tol) tau = fmax(1.618, tau / 1.1);
+    st->tau = tau;
+    // stop test that the reference evaluates at the top of iteration `next`
+    if (fmax(maxfeas, relgap) < st->stop_tol) { st->done = 1; st->stop_reason = 1; }
+    if (next > st->max_iter) { st->done = 1; st->stop_reason = 2; }
+}
+
+// iter == switch_admm (src/solver.cu:681-690)
+__global__ void switch_kernel(DevState* st) {
+    if (st->done) return;
+    st->sig_update_stage_2 = st->sig_update_stage_2 / 2;
+    st->sigscale = st->sigscale * 1.23;
+    st->sgs_KKT = fmax(st->maxfeas, st->relgap);
+    st->best_KKT = st->sgs_KKT;
+}
+
+// iter > switch_admm (src/solver.cu:732-741): decide, then copy
+__global__ void best_decide_kernel(DevState* st) {
+    if (st->done) { st->pad_ = 0; return; }
+    const double cur = fmax(st->maxfeas, st->relgap);
+    if (st->best_KKT > cur) { st->best_KKT = cur; st->pad_ = 1; } else st->pad_ = 0;
+}
+__global__ void best_copy_kernel(const DevState* st, int64_t n, const double* __restrict__ src, double* dst) {
+    if (!st->pad_) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void scale_kernel(int64_t n, double* x, double s) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= s;
+}
+// y <- y ./ normA * s   (dense_vector_div_dense_vector_mul_scalar)  or  y <- y .* normA * s
+__global__ void scale_vec_kernel(int64_t n, double* y, const double* __restrict__ d, double s, int divide) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = divide ? y[i] / d[i] * s : y[i] * d[i] * s;
+}
+__global__ void sub_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
+}
+
+static int ew_grid(int64_t n, int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + kEwThreads - 1) / kEwThreads, (int64_t)sms * 8));
+}
+
+static double host_norm2(const std::vector<double>& v) {
+    // scaled sum of squares (dnrm2 semantics: no overflow for any finite input)
+    double scale = 0.0, ssq = 1.0;
+    for (double x : v) {
+        if (x != 0.0) {
+            const double a = std::fabs(x);
+            if (scale < a) { ssq = 1.0 + ssq * (scale / a) * (scale / a); scale = a; }
+            else ssq += (a / scale) * (a / scale);
+        }
+    }
+    return scale * std::sqrt(ssq);
+}
+
+}  // namespace cuadmm
+
+using namespace cuadmm;
+
+cuadmm_solver::~cuadmm_solver() {
+    cudaSetDevice(device);
+    delete A; delete At; delete ys;
+    if (h_st) cudaFreeHost(h_st);
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_now) cudaEventDestroy(ev_now);
+    for (auto e : prof_ev) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_num*/, int64_t vec_len_, int64_t con_num_,
+                         const int32_t* At_col_ptrs, const int32_t* At_row_ids, const double* At_vals, int64_t At_nnz,
+                         const int32_t* b_idx, const double* b_val, int64_t b_nnz,
+                         const int32_t* C_idx, const double* C_val, int64_t C_nnz,
+                         const int32_t* blk, int64_t mat_num, const double* X0, const double* y0, const double* S0, double sig) {
+    CUADMM_REQUIRE(!initialised, "solver already initialised (one instance per problem, like SDPSolver)");
+    CUADMM_REQUIRE(vec_len_ >= 0 && con_num_ >= 0 && At_nnz >= 0, "negative dimension");
+    CUADMM_REQUIRE(At_col_ptrs && blk, "null argument");
+    CUADMM_REQUIRE(At_col_ptrs[0] == 0 && At_col_ptrs[con_num_] == At_nnz, "At_csc_col_ptrs does not span At_nnz");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        throw Error(CUADMM_ENODEVICE, "no CUDA device available; the solver has no CPU fallback");
+    }
+    if (const char* e = getenv("CUADMM_DEVICE")) device = atoi(e);
+    CUADMM_REQUIRE(device >= 0 && device < cnt, "device index out of range");
+    CUADMM_CUDA(cudaSetDevice(device));
+    vec_len = vec_len_; con_num = con_num_;
+    CUADMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUADMM_CUDA(cudaEventCreate(&ev_start));
+    CUADMM_CUDA(cudaEventCreate(&ev_now));
+    CUADMM_CUDA(cudaEventRecord(ev_start, stream));     // the reference starts its clock in init
+    const auto t0 = std::chrono::steady_clock::now();
+
+    // ---- block plan
+    {
+        int64_t vl = 0;
+        for (int64_t k = 0; k < mat_num; ++k) { CUADMM_REQUIRE(blk[k] >= 1, "block size must be >= 1"); vl += (int64_t)blk[k] * (blk[k] + 1) / 2; }
+        CUADMM_REQUIRE(vl == vec_len, "vec_len does not match the block sizes");
+        plan.reset(new cuadmm_plan());
+        plan->layout.init(blk, mat_num);
+        plan->device = device;
+        plan->build_device();
+    }
+    // ---- A: normalise the constraints (get_normA, src/solver.cu:79-80), same arithmetic
+    std::vector<double> vals(At_vals, At_vals + At_nnz);
+    h_normA.assign(con_num, 1.0);
+    for (int64_t p = 0; p < At_nnz; ++p) CUADMM_REQUIRE(At_row_ids[p] >= 0 && At_row_ids[p] < vec_len, "At row index out of range");
+    for (int64_t i = 0; i < con_num; ++i) {
+        double norm = 0.0;
+        for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) norm += vals[p] * vals[p];
+        norm = std::max(1.0, std::sqrt(norm));
+        h_normA[i] = norm;
+        for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) vals[p] /= norm;
+    }
+    // A in CSR is the CSC of At as given; At in CSR by a counting-sort transpose (csr2csc in the reference)
+    A = spmv_create(con_num, vec_len, At_nnz, At_col_ptrs, At_row_ids, vals.data(), device);
+    std::vector<int32_t> t_rp(vec_len + 1), t_ci(std::max<int64_t>(At_nnz, 1));
+    std::vector<double> t_v(std::max<int64_t>(At_nnz, 1));
+    if (cuadmm_csc_to_csr_host(vec_len, con_num, At_nnz, At_col_ptrs, At_row_ids, vals.data(), t_rp.data(), t_ci.data(), t_v.data()) != 0)
+        throw Error(CUADMM_EINVAL, cuadmm_last_error());
+    At = spmv_create(vec_len, con_num, At_nnz, t_rp.data(), t_ci.data(), t_v.data(), device);
+    // ---- A A^T factorisation (src/solver.cu:91-110), eps = 1e-15
+    ys = ysolve_create(con_num, vec_len, At_nnz, At_col_ptrs, At_row_ids, vals.data(), 1e-15, device);
+
+    // ---- b, C, X, y, S and the scaling (src/solver.cu:113-191)
+    std::vector<double> hb(con_num, 0.0), hC(vec_len, 0.0), hX(vec_len, 0.0), hy(con_num, 0.0), hS(vec_len, 0.0);
+    for (int64_t k = 0; k < b_nnz; ++k) { CUADMM_REQUIRE(b_idx[k] >= 0 && b_idx[k] < con_num, "b index out of range"); hb[b_idx[k]] = b_val[k]; }
+    for (int64_t k = 0; k < C_nnz; ++k) { CUADMM_REQUIRE(C_idx[k] >= 0 && C_idx[k] < vec_len, "C index out of range"); hC[C_idx[k]] = C_val[k]; }
+    if (X0) std::copy(X0, X0 + vec_len, hX.begin());
+    if (y0) std::copy(y0, y0 + con_num, hy.begin());
+    if (S0) std::copy(S0, S0 + vec_len, hS.begin());
+    norm_borg = 1 + host_norm2(hb);
+    norm_Corg = 1 + host_norm2(hC);
+    for (int64_t i = 0; i < con_num; ++i) { hb[i] /= h_normA[i]; hy[i] *= h_normA[i]; }
+    bscale = 1 + host_norm2(hb);
+    Cscale = 1 + host_norm2(hC);
+    objscale = bscale * Cscale;
+    for (auto& v : hb) v /= bscale;
+    for (auto& v : hC) v /= Cscale;
+    for (auto& v : hX) v /= bscale;
+    for (auto& v : hS) v /= Cscale;
+    for (auto& v : hy) v /= Cscale;
+
+    // ---- initial residuals (src/solver.cu:193-228) on the host: init-time, O(nnz)
+    std::vector<double> hRp(con_num), hSmC(vec_len), hRd(vec_len, 0.0);
+    for (int64_t i = 0; i < con_num; ++i) {
+        double acc = 0.0;
+        for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) acc += vals[p] * hX[At_row_ids[p]];
+        hRp[i] = hb[i] - acc;
+    }
+    for (int64_t i = 0; i < con_num; ++i)
+        for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) hRd[At_row_ids[p]] += vals[p] * hy[i];   // Aty
+    double sRp = 0, sRd = 0, cx = 0, by = 0;
+    {
+        std::vector<double> tmp(con_num);
+        for (int64_t i = 0; i < con_num; ++i) tmp[i] = h_normA[i] * hRp[i] * bscale;
+        sRp = host_norm2(tmp);
+        for (int64_t i = 0; i < vec_len; ++i) { hSmC[i] = hS[i] - hC[i]; hRd[i] = (hRd[i] + hSmC[i]) * Cscale; cx += hC[i] * hX[i]; }
+        sRd = host_norm2(hRd);
+        for (int64_t i = 0; i < con_num; ++i) by += hb[i] * hy[i];
+    }
+
+    // ---- device vectors
+    auto up = [&](DevBuf<double>& d, const std::vector<double>& h) { d.alloc(std::max<int64_t>((int64_t)h.size(), 1)); d.upload(h.data(), (int64_t)h.size(), stream); };
+    up(X, hX); up(S, hS); up(y, hy); up(Rp, hRp); up(SmC, hSmC); up(Cd, hC); up(bd, hb); up(normA, h_normA);
+    Rd1.alloc(std::max<int64_t>(vec_len, 1)); Rd.alloc(std::max<int64_t>(vec_len, 1)); Xb.alloc(std::max<int64_t>(vec_len, 1));
+    Xproj.alloc(std::max<int64_t>(vec_len, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1));
+    Rd1.zero(stream); Rd.zero(stream);
+    nA_blocks = spmv_grid(*A); nAt_blocks = spmv_grid(*At); nE_blocks = ew_grid(vec_len, device);
+    partial.alloc(2 * (int64_t)(std::max(nAt_blocks, nE_blocks) + nA_blocks) + 4);
+    partial.zero(stream);
+
+    st.alloc(1);
+    CUADMM_CUDA(cudaMallocHost((void**)&h_st, sizeof(DevState)));
+    memset(h_st, 0, sizeof(DevState));
+    h_st->sig = sig; h_st->tau = 1.95;
+    h_st->errRp = sRp / norm_borg; h_st->errRd = sRd / norm_Corg;
+    h_st->maxfeas = std::max(h_st->errRp, h_st->errRd);
+    h_st->pobj = cx * objscale; h_st->dobj = by * objscale;
+    h_st->relgap = std::fabs(h_st->pobj - h_st->dobj) / (1 + std::fabs(h_st->pobj) + std::fabs(h_st->dobj));
+    h_st->bscale = bscale; h_st->Cscale = Cscale; h_st->objscale = objscale;
+    h_st->norm_borg = norm_borg; h_st->norm_Corg = norm_Corg;
+    h_st->sigmax = 1e3; h_st->sigmin = 1e-3; h_st->ratioconst = 1e0;
+    h_st->prim_win = 0; h_st->dual_win = 0;
+    CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+
+    const int* done_ptr = &st.p->done;
+    spmv_set_done_flag(*A, done_ptr);
+    spmv_set_done_flag(*At, done_ptr);
+    ys->done_flag = done_ptr;
+    plan->done_flag = done_ptr;
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+    init_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    initialised = true;
+}
+
+// Steps 1 .. 5 of iteration `iter` (src/solver.cu:469-799); every kernel is a no-op once st->done
+void cuadmm_solver::enqueue_iteration(int iter, int switch_admm) {
+    const double* scal = &st.p->sig;
+    SpmvEpilogue e;
+    // K1
+    e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
+    spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+    // K2
+    ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
+    // K3
+    e = SpmvEpilogue(); e.mode = 2; e.aux1 = Cd.p; e.aux2 = X.p; e.out2 = Xb.p; e.scal = scal;
+    spmv_launch(*At, 1.0, y.p, 0.0, Rd1.p, e, stream); ++launches;
+    // K4
+    ProjEpilogue pe;
+    pe.X = X.p; pe.Rd1 = Rd1.p; pe.Cd = Cd.p; pe.S = S.p; pe.SmC = SmC.p; pe.sig_ptr = scal;
+    launches += plan->project(Xb.p, Xproj.p, stream, &pe, false);
+    if (iter == switch_admm) {
+        switch_kernel<<<1, 1, 0, stream>>>(st.p); ++launches;
+        CUADMM_CUDA(cudaMemcpyAsync(X_best.p, X.p, sizeof(double) * vec_len, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(y_best.p, y.p, sizeof(double) * con_num, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(S_best.p, S.p, sizeof(double) * vec_len, cudaMemcpyDeviceToDevice, stream));
+    }
+    double* part_rd = partial.p;
+    double* part_rp = partial.p + 2 * (int64_t)std::max(nAt_blocks, nE_blocks);
+    int n_rd = 0;
+    if (iter < switch_admm) {
+        // K5-K7: the sGS second half-step
+        e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
+        spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+        ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
+        e = SpmvEpilogue(); e.mode = 3; e.aux1 = Cd.p; e.aux2 = S.p; e.out2 = X.p; e.scal = scal; e.partial = part_rd;
+        spmv_launch(*At, 1.0, y.p, 0.0, Rd.p, e, stream); ++launches;
+        n_rd = nAt_blocks;
+    } else {
+        if (iter > switch_admm) {
+            const int g = ew_grid(vec_len, device);
+            best_decide_kernel<<<1, 1, 0, stream>>>(st.p);
+            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, vec_len, X.p, X_best.p);
+            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, con_num, y.p, y_best.p);
+            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, vec_len, S.p, S_best.p);
+            launches += 4;
+        }
+        x_update_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(vec_len, Rd1.p, S.p, Cd.p, Rd.p, X.p, st.p, part_rd); ++launches;
+        n_rd = nE_blocks;
+    }
+    // K8
+    e = SpmvEpilogue(); e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = part_rp;
+    spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream); ++launches;
+    // K9
+    scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, part_rd, n_rd, part_rp, nA_blocks, hist.p, hist_cap); ++launches;
+    CUADMM_CUDA(cudaGetLastError());
+}
+
+// what the reference still executes at the top of the iteration in which it breaks
+// (step 1 and step 2a, src/solver.cu:478-528): y is overwritten by the next half-step.
+void cuadmm_solver::enqueue_half_step() {
+    const double* scal = &st.p->sig;
+    SpmvEpilogue e;
+    e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
+    spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+    ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
+}
+
+static bool is_log_iter(int iter) { return (iter <= 200 && iter % 50 == 1) || (iter > 200 && iter % 100 == 1); }
+
+void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshold, int sig_update_stage_1,
+                          int sig_update_stage_2, int switch_admm, double sigscale, bool if_first) {
+    CUADMM_REQUIRE(initialised, "solve() before init()");
+    CUADMM_REQUIRE(max_iter >= 0, "max_iter < 0");
+    CUADMM_REQUIRE(sig_update_stage_1 >= 1 && sig_update_stage_2 >= 1, "sig_update_stage must be >= 1");
+    CUADMM_CUDA(cudaSetDevice(device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t n = vec_len, m = con_num;
+    const int gv = ew_grid(n, device), gm = ew_grid(m, device);
+    if (switch_admm <= max_iter + 1 && X_best.n < std::max<int64_t>(n, 1)) {
+        X_best.alloc(std::max<int64_t>(n, 1)); y_best.alloc(std::max<int64_t>(m, 1)); S_best.alloc(std::max<int64_t>(n, 1));
+    }
+    hist_cap = (int64_t)max_iter + 1;
+    hist.alloc(8 * hist_cap);
+    info_iter_num = 0;
+
+    // state for this call
+    CUADMM_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+    if (!if_first) {
+        // second call: X, y, S were replaced by unscaled values (src/solver.cu:385-409)
+        scale_vec_kernel<<<gm, 256, 0, stream>>>(m, y.p, normA.p, 1.0 / Cscale, 0);
+        scale_kernel<<<gv, 256, 0, stream>>>(n, X.p, 1.0 / bscale);
+        scale_kernel<<<gv, 256, 0, stream>>>(n, S.p, 1.0 / Cscale);
+        sub_kernel<<<gv, 256, 0, stream>>>(n, S.p, Cd.p, SmC.p);
+        h_st->done = 0;
+        CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+        SpmvEpilogue e; e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = partial.p;
+        spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream);
+        launches += 5;
+    }
+    h_st->iter = 1;
+    h_st->max_iter = max_iter; h_st->stop_tol = stop_tol;
+    h_st->sig_update_threshold = sig_update_threshold;
+    h_st->sig_update_stage_1 = sig_update_stage_1; h_st->sig_update_stage_2 = sig_update_stage_2;
+    h_st->switch_admm = switch_admm; h_st->sigscale = sigscale;
+    h_st->tau = (1 < switch_admm) ? 1.95 : 1.618;
+    if (h_st->errRd < stop_tol) h_st->tau = std::max(1.618, h_st->tau / 1.1);
+    // the reference leaves best_KKT uninitialised when switch_admm < 1 and then restores garbage;
+    // here the best iterate is tracked from the first iteration in that case
+    if (switch_admm < 1) h_st->best_KKT = INFINITY;
+    h_st->done = 0; h_st->stop_reason = 0;
+    if (std::max(h_st->maxfeas, h_st->relgap) < stop_tol) { h_st->done = 1; h_st->stop_reason = 1; }
+    if (1 > max_iter) { h_st->done = 1; h_st->stop_reason = 2; }
+    CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+
+    if (verbose) {
+        printf("\n -------------------------------------------------------------------------------");
+        printf("\n                                    cuADMM");
+        printf("\n -------------------------------------------------------------------------------");
+        printf("\n norm of C = %2.1e, norm of b = %2.1e\n", norm_Corg, norm_borg);
+        printf("\n  it. | p infeas d infeas | primal obj.   dual obj. rel. gap |  time |   sigma | \n");
+        printf(" -------------------------------------------------------------------------------\n");
+    }
+    int it = 1;           // next iteration to enqueue
+    int stop_iter = 0;
+    while (true) {
+        CUADMM_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+        CUADMM_CUDA(cudaEventRecord(ev_now, stream));
+        CUADMM_CUDA(cudaStreamSynchronize(stream));
+        const bool done = h_st->done != 0;
+        const int cur = h_st->iter;
+        if (verbose && (done || is_log_iter(cur))) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev_start, ev_now);
+            printf(" %4d | %3.2e %3.2e | %- 5.4e %- 5.4e %3.2e | %5.1f | %2.1e |\n",
+                   cur - 1, h_st->errRp, h_st->errRd, h_st->pobj, h_st->dobj, h_st->relgap, ms / 1000.0, h_st->sig);
+            fflush(stdout);
+        }
+        if (done) { stop_iter = cur; break; }
+        int target = it + 1;
+        while (!is_log_iter(target) && target <= max_iter) ++target;
+        for (int k = it; k < target; ++k) enqueue_iteration(k, switch_admm);
+        it = target;
+    }
+    info_iter_num = stop_iter - 1;
+
+    // the partial iteration the reference runs before it breaks, then the best-iterate restore
+    h_st->done = 0;
+    CUADMM_CUDA(cudaMemcpyAsync(&st.p->done, &h_st->done, sizeof(int), cudaMemcpyHostToDevice, stream));
+    enqueue_half_step();
+    if (stop_iter > switch_admm && X_best.n >= std::max<int64_t>(n, 1) && (switch_admm >= 1 || stop_iter > 1)) {
+        CUADMM_CUDA(cudaMemcpyAsync(X.p, X_best.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(y.p, y_best.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(S.p, S_best.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+        CUADMM_CUDA(cudaStreamSynchronize(stream));
+        if (verbose) printf("best max KKT residual after switch  = %2.1e \n", h_st->best_KKT);
+    }
+    h_st->done = 1;
+    CUADMM_CUDA(cudaMemcpyAsync(&st.p->done, &h_st->done, sizeof(int), cudaMemcpyHostToDevice, stream));
+    // unscale (src/solver.cu:814-816)
+    scale_kernel<<<gv, 256, 0, stream>>>(n, X.p, bscale);
+    scale_vec_kernel<<<gm, 256, 0, stream>>>(m, y.p, normA.p, Cscale, 1);
+    scale_kernel<<<gv, 256, 0, stream>>>(n, S.p, Cscale);
+    launches += 3;
+    h_hist.assign(8 * (size_t)std::max<int64_t>(info_iter_num, 0), 0.0);
+    for (int q = 0; q < 8 && info_iter_num > 0; ++q)
+        CUADMM_CUDA(cudaMemcpyAsync(h_hist.data() + q * info_iter_num, hist.p + q * hist_cap, sizeof(double) * info_iter_num,
+                                    cudaMemcpyDeviceToHost, stream));
+    CUADMM_CUDA(cudaEventRecord(ev_now, stream));
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_start, ev_now);
+    total_time = ms / 1000.0;
+    solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (verbose) {
+        printf("\n -------------------------------------------------------------------------------\n\n");
+        printf("%s\n", h_st->stop_reason == 2 ? "Solver ended: maximum iteration reached" : "Solver ended: converged.");
+        printf("\n primal infeasibility = %2.1e \n dual   infeasibility = %2.1e \n relative gap         = %2.1e",
+               h_st->errRp, h_st->errRd, h_st->relgap);
+        printf("\n primal objective = %- 9.8e \n dual   objective = %- 9.8e", h_st->pobj, h_st->dobj);
+        printf("\n\n time per iteration = %2.4fs \n total time         = %2.1fs", total_time / std::max(stop_iter, 1), total_time);
+        printf("\n -------------------------------------------------------------------------------\n\n");
+        fflush(stdout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int cuadmm_solver_create(cuadmm_solver_t** out) {
+    return guarded([&] { CUADMM_REQUIRE(out, "out is null"); *out = new cuadmm_solver(); });
+}
+void cuadmm_solver_destroy(cuadmm_solver_t* s) { delete s; }
+int cuadmm_solver_set_verbose(cuadmm_solver_t* s, int verbose) {
+    return guarded([&] { CUADMM_REQUIRE(s, "solver is null"); s->verbose = verbose != 0; });
+}
+
+int cuadmm_solver_init(cuadmm_solver_t* s, int eig_stream_num_per_gpu, int cpu_eig_thread_num, int64_t vec_len, int64_t con_num,
+        const int32_t* At_csc_col_ptrs, const int32_t* At_csc_row_ids, const double* At_csc_vals, int64_t At_nnz,
+        const int32_t* b_indices, const double* b_vals, int64_t b_nnz,
+        const int32_t* C_indices, const double* C_vals, int64_t C_nnz,
+        const int32_t* blk_vals, int64_t mat_num, const double* X_vals, const double* y_vals, const double* S_vals, double sig) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s, "solver is null");
+        s->init(eig_stream_num_per_gpu, cpu_eig_thread_num, vec_len, con_num, At_csc_col_ptrs, At_csc_row_ids, At_csc_vals, At_nnz,
+                b_indices, b_vals, b_nnz, C_indices, C_vals, C_nnz, blk_vals, mat_num, X_vals, y_vals, S_vals, sig);
+    });
+}
+
+int cuadmm_solver_init_from_problem(cuadmm_solver_t* s, const cuadmm_problem_t* p, int eig_stream_num_per_gpu,
+                                    int cpu_eig_thread_num, double sig) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && p, "null argument");
+        const Problem& q = p->prob;
+        s->init(eig_stream_num_per_gpu, cpu_eig_thread_num, q.vec_len, q.con_num, q.At_csc_col_ptrs.data(), q.At_csc_row_ids.data(),
+                q.At_csc_vals.data(), q.At_nnz, q.b_indices.data(), q.b_vals.data(), q.b_nnz, q.C_indices.data(), q.C_vals.data(),
+                q.C_nnz, q.blk_vals.data(), q.mat_num, q.X_vals.empty() ? nullptr : q.X_vals.data(),
+                q.y_vals.empty() ? nullptr : q.y_vals.data(), q.S_vals.empty() ? nullptr : q.S_vals.data(), sig);
+    });
+}
+
+int cuadmm_solver_solve(cuadmm_solver_t* s, int max_iter, double stop_tol, int sig_update_threshold, int sig_update_stage_1,
+                        int sig_update_stage_2, int switch_admm, double sigscale, int if_first) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s, "solver is null");
+        s->solve(max_iter, stop_tol, sig_update_threshold, sig_update_stage_1, sig_update_stage_2, switch_admm, sigscale, if_first != 0);
+    });
+}
+
+static void get_vec(cuadmm_solver_t* s, const DevBuf<double>& d, int64_t n, double* h) {
+    CUADMM_REQUIRE(s && h, "null argument");
+    CUADMM_REQUIRE(s->initialised, "solver not initialised");
+    CUADMM_CUDA(cudaSetDevice(s->device));
+    d.download(h, n, s->stream);
+    CUADMM_CUDA(cudaStreamSynchronize(s->stream));
+}
+int cuadmm_solver_get_X(cuadmm_solver_t* s, double* h) { return guarded([&] { get_vec(s, s->X, s->vec_len, h); }); }
+int cuadmm_solver_get_y(cuadmm_solver_t* s, double* h) { return guarded([&] { get_vec(s, s->y, s->con_num, h); }); }
+int cuadmm_solver_get_S(cuadmm_solver_t* s, double* h) { return guarded([&] { get_vec(s, s->S, s->vec_len, h); }); }
+
+int cuadmm_solver_set_XyS(cuadmm_solver_t* s, const double* h_X, const double* h_y, const double* h_S, double sig) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && s->initialised, "solver not initialised");
+        CUADMM_CUDA(cudaSetDevice(s->device));
+        if (h_X) s->X.upload(h_X, s->vec_len, s->stream);
+        if (h_y) s->y.upload(h_y, s->con_num, s->stream);
+        if (h_S) s->S.upload(h_S, s->vec_len, s->stream);
+        CUADMM_CUDA(cudaMemcpyAsync(&s->st.p->sig, &sig, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUADMM_CUDA(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int64_t cuadmm_solver_iter_num(const cuadmm_solver_t* s) { return s ? s->info_iter_num : -1; }
+
+int cuadmm_solver_history(const cuadmm_solver_t* s, int which, double* out, int64_t cap) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && out, "null argument");
+        CUADMM_REQUIRE(which >= 0 && which < 8, "which out of range");
+        const int64_t n = std::min<int64_t>(cap, s->info_iter_num);
+        for (int64_t k = 0; k < n; ++k) out[k] = s->h_hist[(size_t)which * s->info_iter_num + k];
+    });
+}
+
+int cuadmm_solver_times(const cuadmm_solver_t* s, double out[8]) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && out, "null argument");
+        out[0] = s->total_time; out[1] = s->init_time; out[2] = s->solve_time; out[3] = s->proj_time;
+        out[4] = s->ysolve_time; out[5] = s->spmv_time; out[6] = 0; out[7] = 0;
+    });
+}
+
+int64_t cuadmm_solver_launches(const cuadmm_solver_t* s) { return s ? s->launches : -1; }
+
+int cuadmm_solve_matlab_like(int eig_stream_num_per_gpu, int max_iter, double stop_tol, int64_t vec_len, int64_t con_num,
+        const int64_t* At_jc, const int64_t* At_ir, const double* At_pr,
+        const int64_t* b_ir, const double* b_pr, int64_t b_nnz, const int64_t* C_ir, const double* C_pr, int64_t C_nnz,
+        const double* blk_vec, int64_t mat_num, const double* X0, const double* y0, const double* S0, double sig,
+        int sig_update_threshold, int sig_update_stage_1, int sig_update_stage_2, int switch_admm, double sigscale,
+        double* X, double* y, double* S, int64_t* iter_num, double* info, double* total_time) {
+    return guarded([&] {
+        CUADMM_REQUIRE(At_jc && blk_vec && X && y && S, "null argument");
+        // the MEX narrows MATLAB's size_t indices to int32 (MATLAB/cuadmm_MATLAB.cu:48-51,73-88)
+        const int64_t nnz = At_jc[con_num];
+        CUADMM_REQUIRE(nnz <= INT32_MAX && vec_len <= INT32_MAX, "problem exceeds the int32 indices of the reference interface");
+        std::vector<int32_t> cp(con_num + 1), ri(nnz), bi(b_nnz), ci(C_nnz), blk(mat_num);
+        for (int64_t i = 0; i <= con_num; ++i) cp[i] = (int32_t)At_jc[i];
+        for (int64_t p = 0; p < nnz; ++p) ri[p] = (int32_t)At_ir[p];
+        for (int64_t k = 0; k < b_nnz; ++k) bi[k] = (int32_t)b_ir[k];
+        for (int64_t k = 0; k < C_nnz; ++k) ci[k] = (int32_t)C_ir[k];
+        for (int64_t k = 0; k < mat_num; ++k) blk[k] = (int32_t)blk_vec[k];
+        cuadmm_solver s;
+        s.init(eig_stream_num_per_gpu, 30, vec_len, con_num, cp.data(), ri.data(), At_pr, nnz, bi.data(), b_pr, b_nnz,
+               ci.data(), C_pr, C_nnz, blk.data(), mat_num, X0, y0, S0, sig);
+        s.solve(max_iter, stop_tol, sig_update_threshold, sig_update_stage_1, sig_update_stage_2, switch_admm, sigscale, true);
+        s.X.download(X, vec_len, s.stream); s.y.download(y, con_num, s.stream); s.S.download(S, vec_len, s.stream);
+        CUADMM_CUDA(cudaStreamSynchronize(s.stream));
+        if (iter_num) *iter_num = s.info_iter_num;
+        if (info) {
+            const int64_t cap = (int64_t)max_iter + 1;
+            for (int q = 0; q < 8; ++q)
+                for (int64_t k = 0; k < cap; ++k)
+                    info[q * cap + k] = k < s.info_iter_num ? s.h_hist[(size_t)q * s.info_iter_num + k] : 0.0;
+        }
+        if (total_time) *total_time = s.total_time;
+    });
+}
+
+}  // extern "C"

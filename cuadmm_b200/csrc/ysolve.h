@@ -1,0 +1,52 @@
+// ysolve.h — device-resident  y = (A A^T + eps I)^-1 rhs.
+#pragma once
+#include "common.h"
+#include "chol_host.h"
+
+namespace cuadmm {
+
+// One pull-style sparse triangular sweep: unknown u (processed in `sched` order) is
+//   x[u] = (rhs[u] - sum_p val[p] * x[dep[p]]) * inv_diag[u]
+// Forward solve with L: u = row, deps = columns < u.  Backward solve with L^T: u = column,
+// deps = rows > u.  Same kernel for both; dependencies are awaited through per-unknown flags
+// (synchronisation-free SpTRSV), so one launch covers the whole dependency DAG.
+struct TriSweep {
+    int64_t n_unknowns = 0;       // unknowns solved by this sweep
+    int64_t nnz = 0;
+    DevBuf<int64_t> ptr;          // per unknown (indexed by unknown id)
+    DevBuf<int32_t> dep;
+    DevBuf<double> val;
+    DevBuf<double> inv_diag;
+    DevBuf<int32_t> sched;        // slots: unknown ids in level order, -1 padding
+    int64_t n_slots = 0;
+    int group = 32;               // lanes per unknown
+    int levels = 0;
+    int grid = 0;
+};
+
+}  // namespace cuadmm
+
+struct cuadmm_ysolve_s {
+    int device = -1;
+    int64_t m = 0;
+    int64_t n_lead = 0, n_tail = 0;
+    int64_t nnz_aat = 0, nnz_L = 0, n_deficient = 0;
+    cuadmm::TriSweep fwd, bwd;
+    cuadmm::DevBuf<int32_t> perm;      // perm[new] = old
+    cuadmm::DevBuf<double> z;          // forward result (permuted order)
+    cuadmm::DevBuf<double> x;          // backward result (permuted order)
+    cuadmm::DevBuf<int32_t> flags;     // fwd flags [0,m) + bwd flags [m, 2m)
+    // dense tail: inverse of the trailing Cholesky block, row-major lower and its transpose
+    cuadmm::DevBuf<double> tail_inv, tail_inv_t, tail_tmp;
+    cuadmm::DevBuf<double> d_rhs, d_y; // staging for the host entry
+    std::vector<int32_t> h_perm;
+    const int* done_flag = nullptr;
+    int launches_per_solve = 0;
+    int64_t alg_bytes = 0;
+    void solve(const double* d_rhs, double* d_y, cudaStream_t stream);
+};
+
+namespace cuadmm {
+cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const int32_t* rowptr, const int32_t* colind,
+                               const double* val, double eps, int device);
+}
