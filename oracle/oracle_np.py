@@ -233,8 +233,17 @@ class ADMMOracle:
     def solve(self, max_iter, stop_tol, sig_update_threshold=500, sig_update_stage_1=50, sig_update_stage_2=100,
               switch_admm=11000, sigscale=1.05):
         it_done = 0
+        best = None
+        best_KKT = np.inf if switch_admm < 1 else None
+        stop_it = max_iter + 1
         for it in range(1, max_iter + 2):
             if max(self.maxfeas, self.relgap) < stop_tol or it > max_iter:       # solver.cu:419-428
+                stop_it = it
+                # the reference still runs step 1 before breaking (:478-500 precede the break at :567-576)
+                rhsy = self.Rp / self.sig - self.A @ self.SmC
+                self.y = self.lin.solve(rhsy)
+                if it > switch_admm and best is not None:                       # :568-573 restore best
+                    self.X, self.y, self.S = best
                 break
             rhsy = self.Rp / self.sig - self.A @ self.SmC                       # :478-482
             self.y = self.lin.solve(rhsy)                                       # :487-500
@@ -246,10 +255,16 @@ class ADMMOracle:
             if it == switch_admm:                                               # :681-690
                 sig_update_stage_2 = sig_update_stage_2 // 2
                 sigscale = sigscale * 1.23
+                best_KKT = max(self.maxfeas, self.relgap)
+                best = (self.X.copy(), self.y.copy(), self.S.copy())
             if it < switch_admm:                                                # :693-729
                 rhsy = self.Rp / self.sig - self.A @ self.SmC
                 self.y = self.lin.solve(rhsy)
                 Rd1 = self.At @ self.y - self.C
+            if it > switch_admm:                                                # :732-741
+                if best_KKT > max(self.maxfeas, self.relgap):
+                    best = (self.X.copy(), self.y.copy(), self.S.copy())
+                    best_KKT = max(self.maxfeas, self.relgap)
             self.Rd = Rd1 + self.S                                              # :746
             tau = 1.95 if it < switch_admm else 1.618                           # :747-754
             if self.errRd < stop_tol:

@@ -111,8 +111,14 @@ def test_scaling_invariance_and_extremes():
     x = random_svec(blk, seed=9)
     p = cu.Plan(blk)
     base = p.project_host(x)
-    for s in [1e-300, 1e-150, 1e-30, 1e30, 1e150, 1e300]:
-        assert np.allclose(p.project_host(x * s), base * s, rtol=1e-11, atol=0)
+    # exact power-of-two scalings: the kernel prescales by 2^-exponent, so nothing may over/underflow
+    for e in [-900, -500, -60, 60, 500, 900]:
+        out = p.project_host(np.ldexp(x, e))
+        assert np.linalg.norm(np.ldexp(out, -e) - base) <= 1e-13 * np.linalg.norm(base), e
+    for s10 in [1e-150, 1e150]:
+        out = p.project_host(x * s10)
+        assert np.linalg.norm(out / s10 - base) <= 1e-12 * np.linalg.norm(base)
+    assert np.all(np.isnan(p.project_host(np.full_like(x, np.nan))))
 
 
 def test_empty_and_ragged():

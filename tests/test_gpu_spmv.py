@@ -10,13 +10,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _rand_csr(rows, cols, density, seed, long_rows=0):
-    M = sp.random(rows, cols, density=density, random_state=seed, format="lil")
+    """random CSR built straight from COO triplets (LIL assignment is far too slow at size)"""
     rng = np.random.default_rng(seed)
-    for i in range(long_rows):
-        r = rng.integers(0, rows)
+    nnz = max(1, int(rows * cols * density))
+    r = rng.integers(0, rows, nnz); c = rng.integers(0, cols, nnz); v = rng.standard_normal(nnz)
+    for _ in range(long_rows):
         k = min(cols, 3000)
-        M[r, rng.choice(cols, k, replace=False)] = rng.standard_normal(k)
-    M = M.tocsr(); M.sort_indices()
+        r = np.concatenate([r, np.full(k, rng.integers(0, rows))])
+        c = np.concatenate([c, rng.choice(cols, k, replace=False)])
+        v = np.concatenate([v, rng.standard_normal(k)])
+    M = sp.csr_matrix((v, (r, c)), shape=(rows, cols))
+    M.sum_duplicates(); M.sort_indices()
     return M
 
 
