@@ -314,6 +314,8 @@ _maybe("cuadmm_solver_iter_num", C.c_int64, vp)
 _maybe("cuadmm_solver_history", C.c_int, vp, C.c_int, c_f64p, C.c_int64)
 _maybe("cuadmm_solver_times", C.c_int, vp, c_f64p)
 _maybe("cuadmm_solver_launches", C.c_int64, vp)
+_maybe("cuadmm_solver_run_iterations", C.c_int, vp, C.c_int, C.c_int, C.c_int, c_f64p)
+_maybe("cuadmm_solver_ysolve_stats", C.c_int, vp, c_i64p)
 _maybe("cuadmm_solver_init_from_problem", C.c_int, vp, vp, C.c_int, C.c_int, C.c_double)
 
 
@@ -433,3 +435,25 @@ class Solver:
     @property
     def launches(self):
         return lib.cuadmm_solver_launches(self.h)
+
+    def run_iterations(self, n, sgs=True, profile=False):
+        """measurement hook: n iterations from the current state, stop test off; device ms by CUDA events"""
+        out = np.zeros(4)
+        _check(lib.cuadmm_solver_run_iterations(self.h, int(n), int(sgs), int(profile), _p(out, c_f64p)))
+        return dict(total_ms=out[0], projection_ms=out[1], ysolve_ms=out[2], other_ms=out[3])
+
+    def set_XyS(self, X, y, S, sig):
+        X, y, S = _f64(X), _f64(y), _f64(S)
+        _check(lib.cuadmm_solver_set_XyS(self.h, _p(X, c_f64p), _p(y, c_f64p), _p(S, c_f64p), float(sig)))
+
+    def get_into(self, X, y, S):
+        """D2H of X, y, S into caller-provided (e.g. pinned) arrays"""
+        _check(lib.cuadmm_solver_get_X(self.h, _p(X, c_f64p)))
+        _check(lib.cuadmm_solver_get_y(self.h, _p(y, c_f64p)))
+        _check(lib.cuadmm_solver_get_S(self.h, _p(S, c_f64p)))
+
+    def ysolve_stats(self):
+        s = np.zeros(8, np.int64)
+        _check(lib.cuadmm_solver_ysolve_stats(self.h, _p(s, c_i64p)))
+        return dict(nnz_AAt=int(s[0]), nnz_L=int(s[1]), levels=int(s[2]), dense_tail=int(s[3]),
+                    launches=int(s[4]), bytes=int(s[5]), deficient=int(s[6]))

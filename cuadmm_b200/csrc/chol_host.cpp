@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <stdlib.h>
+#include <string.h>
 
 namespace cuadmm {
 
@@ -92,9 +94,16 @@ std::vector<int32_t> min_degree_order(const SymCsc& M) {
     std::vector<int64_t> mark(n, -1), wstamp(n, -1), w(n, 0);
     std::vector<int32_t> Lp;
     int64_t mindeg = 0;
-    for (int64_t k = 0; k < n; ++k) {
-        while (head[mindeg] < 0) ++mindeg;
-        const int32_t p = head[mindeg];
+    // Multiple elimination in rounds with a relaxed degree threshold: every round eliminates an
+    // INDEPENDENT set of variables whose degree is within `slack` of the minimum.  Independent pivots
+    // do not depend on each other in the triangular solves, so the depth of the solve DAG is bounded by
+    // the number of rounds: on chain-like constraint graphs (moment relaxations over a time horizon)
+    // this is cyclic reduction, depth O(log n), where plain minimum degree eats the chain from its
+    // ends and produces depth O(n).  The GPU sweeps are latency-bound in that depth.
+    std::vector<int64_t> blocked(n, -1);
+    std::vector<int32_t> cands;
+    int64_t k = 0, round = 0;
+    auto eliminate = [&](const int32_t p) {
         list_remove(p);
         perm[k] = p;
         // ---- L_p = (A_p  U  union of L_e, e in E_p) \ {p}
@@ -157,7 +166,26 @@ std::vector<int32_t> min_degree_order(const SymCsc& M) {
         members[p] = Lp;
         for (int32_t i : Lp) {
             list_insert(i);
+            blocked[i] = round;
             if (degree[i] < mindeg) mindeg = degree[i];
+        }
+        ++k;
+    };
+    const char* mode_env = getenv("CUADMM_MD_MODE");          // "classic": one pivot per round (tuning only)
+    const bool classic = mode_env && !strcmp(mode_env, "classic");
+    const char* slack_env = getenv("CUADMM_MD_SLACK");        // relative slack in percent (default 25)
+    const int64_t slack_pct = slack_env ? atoll(slack_env) : 25;
+    while (k < n) {
+        ++round;
+        while (head[mindeg] < 0) ++mindeg;
+        if (classic) { eliminate(head[mindeg]); continue; }
+        const int64_t limit = std::min<int64_t>(n, mindeg + std::max<int64_t>(1, mindeg * slack_pct / 100));
+        cands.clear();
+        for (int64_t d = mindeg; d <= limit; ++d)
+            for (int32_t i = head[d]; i >= 0; i = next[i]) cands.push_back(i);
+        for (int32_t p : cands) {
+            if (status[p] != VAR || blocked[p] == round || degree[p] > limit) continue;
+            eliminate(p);
         }
     }
     return perm;
@@ -265,6 +293,45 @@ void chol_symbolic(const SymCsc& M, const std::vector<int32_t>& perm, CholFactor
         }
     }
     if (permuted) *permuted = std::move(C);
+}
+
+std::vector<int32_t> postorder_perm(const SymCsc& M, const std::vector<int32_t>& perm) {
+    CholFactor F;
+    chol_symbolic(M, perm, F, nullptr);
+    const int64_t n = F.n;
+    // children lists (ascending), iterative DFS
+    std::vector<int32_t> head(n, -1), nxt(n, -1);
+    for (int64_t j = n - 1; j >= 0; --j) if (F.parent[j] >= 0) { nxt[j] = head[F.parent[j]]; head[F.parent[j]] = (int32_t)j; }
+    std::vector<int32_t> post; post.reserve(n);
+    std::vector<int32_t> stack;
+    for (int64_t r = 0; r < n; ++r) {
+        if (F.parent[r] >= 0) continue;
+        stack.push_back((int32_t)r);
+        while (!stack.empty()) {
+            const int32_t v = stack.back();
+            const int32_t c = head[v];
+            if (c >= 0) { head[v] = nxt[c]; stack.push_back(c); }
+            else { post.push_back(v); stack.pop_back(); }
+        }
+    }
+    std::vector<int32_t> out(n);
+    for (int64_t k = 0; k < n; ++k) out[k] = perm[post[k]];
+    return out;
+}
+
+std::vector<int64_t> find_supernodes(const CholFactor& F, int64_t max_size) {
+    const int64_t n = F.n;
+    std::vector<int64_t> sn;
+    sn.push_back(0);
+    std::vector<int32_t> nchild(n, 0);
+    for (int64_t j = 0; j < n; ++j) if (F.parent[j] >= 0) nchild[F.parent[j]]++;
+    for (int64_t j = 1; j < n; ++j) {
+        const int64_t cprev = F.Lp[j] - F.Lp[j - 1], ccur = F.Lp[j + 1] - F.Lp[j];
+        const bool join = F.parent[j - 1] == j && ccur == cprev - 1 && nchild[j] == 1 && (j - sn.back()) < max_size;
+        if (!join) sn.push_back(j);
+    }
+    if (n > 0) sn.push_back(n);
+    return sn;
 }
 
 // ------------------------------------------------------------------------------------------

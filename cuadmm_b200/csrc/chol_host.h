@@ -37,6 +37,15 @@ struct CholFactor {
     int64_t nnz() const { return Lp.empty() ? 0 : Lp[n]; }
 };
 
+// etree postorder of a fill-reducing permutation: returns perm' with the same fill whose elimination
+// tree is postordered (children before parents, subtrees contiguous), so that columns with nested
+// structure become adjacent and form supernodes.
+std::vector<int32_t> postorder_perm(const SymCsc& M, const std::vector<int32_t>& perm);
+
+// fundamental supernodes of a postordered factor: sn_ptr (size nsn+1) column ranges.  A column joins
+// the previous one when it is its etree parent and has exactly one entry less; max_size caps the width.
+std::vector<int64_t> find_supernodes(const CholFactor& F, int64_t max_size);
+
 // symbolic (pattern + etree) only: fills everything but Lx
 void chol_symbolic(const SymCsc& M, const std::vector<int32_t>& perm, CholFactor& F, SymCsc* permuted = nullptr);
 // numeric up-looking factorisation of rows [0, n_lead); for rows >= n_lead only the entries in

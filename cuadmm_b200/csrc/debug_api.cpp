@@ -19,6 +19,7 @@ int cuadmm_debug_chol_solve(int64_t m, int64_t ncols, const int32_t* rowptr, con
     return guarded([&] {
         SymCsc M = form_aat(m, ncols, rowptr, colind, val, eps);
         std::vector<int32_t> perm = min_degree_order(M);
+        perm = postorder_perm(M, perm);
         CholFactor F; SymCsc C;
         chol_symbolic(M, perm, F, &C);
         const int64_t n_lead = std::max<int64_t>(0, std::min<int64_t>(m, (int64_t)(n_lead_frac * (double)m)));
@@ -60,7 +61,42 @@ int cuadmm_debug_chol_solve(int64_t m, int64_t ncols, const int32_t* rowptr, con
         }
         for (int64_t k = 0; k < m; ++k) y[F.perm[k]] = z[k];
         if (perm_out) std::copy(F.perm.begin(), F.perm.end(), perm_out);
-        if (stats) { stats[0] = M.p[m]; stats[1] = F.nnz(); stats[2] = F.n_deficient; }
+        if (stats) {
+            stats[0] = M.p[m]; stats[1] = F.nnz(); stats[2] = F.n_deficient;
+            // depth of the forward-solve dependency DAG, and how many rows sit in levels narrower than 8
+            std::vector<int32_t> lev(m, 0);
+            int32_t depth = 0;
+            for (int64_t j = 0; j < m; ++j) {
+                for (int64_t p = F.Lp[j] + 1; p < F.Lp[j + 1]; ++p) lev[F.Li[p]] = std::max(lev[F.Li[p]], lev[j] + 1);
+                depth = std::max(depth, lev[j] + 1);
+            }
+            stats[3] = depth;
+            std::vector<int64_t> cnt(depth + 1, 0);
+            for (int64_t j = 0; j < m; ++j) cnt[lev[j]]++;
+            int64_t narrow = 0;
+            for (int32_t l = 0; l < depth; ++l) if (cnt[l] < 8) narrow += cnt[l];
+            stats[4] = narrow;
+            // supernodal depth: all columns of a fundamental supernode share one level
+            std::vector<int64_t> sn = find_supernodes(F, 256);
+            const int64_t nsn = (int64_t)sn.size() - 1;
+            std::vector<int32_t> snof(m, 0), slev(std::max<int64_t>(nsn, 1), 0);
+            for (int64_t s = 0; s < nsn; ++s) for (int64_t j = sn[s]; j < sn[s + 1]; ++j) snof[j] = (int32_t)s;
+            int32_t sdepth = 0;
+            for (int64_t s = 0; s < nsn; ++s) {
+                for (int64_t j = sn[s]; j < sn[s + 1]; ++j)
+                    for (int64_t p = F.Lp[j] + 1; p < F.Lp[j + 1]; ++p) {
+                        const int32_t t = snof[F.Li[p]];
+                        if (t != s) slev[t] = std::max(slev[t], slev[s] + 1);
+                    }
+                sdepth = std::max(sdepth, slev[s] + 1);
+            }
+            stats[5] = nsn; stats[6] = sdepth;
+            std::vector<int64_t> scnt(sdepth + 1, 0);
+            for (int64_t s = 0; s < nsn; ++s) scnt[slev[s]] += sn[s + 1] - sn[s];
+            int64_t deep_rows = 0;   // rows in supernodal levels >= 48
+            for (int32_t l = 48; l < sdepth; ++l) deep_rows += scnt[l];
+            stats[7] = deep_rows;
+        }
     });
 }
 

@@ -303,21 +303,34 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
 }
 
 // Steps 1 .. 5 of iteration `iter` (src/solver.cu:469-799); every kernel is a no-op once st->done
-void cuadmm_solver::enqueue_iteration(int iter, int switch_admm) {
+void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
     const double* scal = &st.p->sig;
     SpmvEpilogue e;
+    // profile mode: 6 events per iteration bracket the y-solves and the projection stage
+    auto mark = [&](int k) {
+        if (!prof) return;
+        cudaEvent_t ev;
+        CUADMM_CUDA(cudaEventCreate(&ev));
+        CUADMM_CUDA(cudaEventRecord(ev, stream));
+        prof_ev.push_back(ev);
+        (void)k;
+    };
     // K1
     e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
     spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
     // K2
+    mark(0);
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
+    mark(1);
     // K3
     e = SpmvEpilogue(); e.mode = 2; e.aux1 = Cd.p; e.aux2 = X.p; e.out2 = Xb.p; e.scal = scal;
     spmv_launch(*At, 1.0, y.p, 0.0, Rd1.p, e, stream); ++launches;
     // K4
     ProjEpilogue pe;
     pe.X = X.p; pe.Rd1 = Rd1.p; pe.Cd = Cd.p; pe.S = S.p; pe.SmC = SmC.p; pe.sig_ptr = scal;
+    mark(2);
     launches += plan->project(Xb.p, Xproj.p, stream, &pe, false);
+    mark(3);
     if (iter == switch_admm) {
         switch_kernel<<<1, 1, 0, stream>>>(st.p); ++launches;
         CUADMM_CUDA(cudaMemcpyAsync(X_best.p, X.p, sizeof(double) * vec_len, cudaMemcpyDeviceToDevice, stream));
@@ -331,7 +344,9 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm) {
         // K5-K7: the sGS second half-step
         e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
         spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+        mark(4);
         ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
+        mark(5);
         e = SpmvEpilogue(); e.mode = 3; e.aux1 = Cd.p; e.aux2 = S.p; e.out2 = X.p; e.scal = scal; e.partial = part_rd;
         spmv_launch(*At, 1.0, y.p, 0.0, Rd.p, e, stream); ++launches;
         n_rd = nAt_blocks;
@@ -344,6 +359,7 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm) {
             best_copy_kernel<<<g, 256, 0, stream>>>(st.p, vec_len, S.p, S_best.p);
             launches += 4;
         }
+        mark(4); mark(5);
         x_update_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(vec_len, Rd1.p, S.p, Cd.p, Rd.p, X.p, st.p, part_rd); ++launches;
         n_rd = nE_blocks;
     }
@@ -365,6 +381,51 @@ void cuadmm_solver::enqueue_half_step() {
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
 }
 
+void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double out_ms[4]) {
+    CUADMM_REQUIRE(initialised && hist.n > 0, "run_iterations() needs init() and one solve() first");
+    CUADMM_CUDA(cudaSetDevice(device));
+    // disable the stop test, keep the reference's sigma cadence running
+    CUADMM_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+    const int first = h_st->iter;
+    h_st->done = 0; h_st->stop_tol = -1.0; h_st->max_iter = 0x7fffffff;
+    const int sw = sgs ? 0x7fffffff : 0;
+    h_st->switch_admm = sw;
+    h_st->tau = sgs ? 1.95 : 1.618;
+    CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+    if (!sgs && X_best.n < std::max<int64_t>(vec_len, 1)) {
+        X_best.alloc(std::max<int64_t>(vec_len, 1)); y_best.alloc(std::max<int64_t>(con_num, 1)); S_best.alloc(std::max<int64_t>(vec_len, 1));
+    }
+    for (auto e : prof_ev) cudaEventDestroy(e);
+    prof_ev.clear();
+    cudaEvent_t e0, e1;
+    CUADMM_CUDA(cudaEventCreate(&e0)); CUADMM_CUDA(cudaEventCreate(&e1));
+    CUADMM_CUDA(cudaEventRecord(e0, stream));
+    for (int k = 0; k < n_iters; ++k) enqueue_iteration(first + k, sw, profile_);
+    CUADMM_CUDA(cudaEventRecord(e1, stream));
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    out_ms[0] = ms; out_ms[1] = out_ms[2] = out_ms[3] = 0.0;
+    if (profile_) {
+        for (size_t i = 0; i + 5 < prof_ev.size(); i += 6) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, prof_ev[i], prof_ev[i + 1]);
+            cudaEventElapsedTime(&b, prof_ev[i + 2], prof_ev[i + 3]);
+            cudaEventElapsedTime(&c, prof_ev[i + 4], prof_ev[i + 5]);
+            out_ms[2] += a + (sgs ? c : 0.f);
+            out_ms[1] += b;
+        }
+        out_ms[3] = out_ms[0] - out_ms[1] - out_ms[2];
+        for (auto e : prof_ev) cudaEventDestroy(e);
+        prof_ev.clear();
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h_st->done = 1;
+    CUADMM_CUDA(cudaMemcpyAsync(&st.p->done, &h_st->done, sizeof(int), cudaMemcpyHostToDevice, stream));
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+}
+
 static bool is_log_iter(int iter) { return (iter <= 200 && iter % 50 == 1) || (iter > 200 && iter % 100 == 1); }
 
 void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshold, int sig_update_stage_1,
@@ -379,8 +440,10 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     if (switch_admm <= max_iter + 1 && X_best.n < std::max<int64_t>(n, 1)) {
         X_best.alloc(std::max<int64_t>(n, 1)); y_best.alloc(std::max<int64_t>(m, 1)); S_best.alloc(std::max<int64_t>(n, 1));
     }
-    hist_cap = (int64_t)max_iter + 1;
-    hist.alloc(8 * hist_cap);
+    if ((int64_t)max_iter + 1 > hist_cap || hist.n == 0) {   // keep the buffer across warm-restart calls
+        hist_cap = (int64_t)max_iter + 1;
+        hist.alloc(8 * hist_cap);
+    }
     info_iter_num = 0;
 
     // state for this call
@@ -574,6 +637,20 @@ int cuadmm_solver_times(const cuadmm_solver_t* s, double out[8]) {
 }
 
 int64_t cuadmm_solver_launches(const cuadmm_solver_t* s) { return s ? s->launches : -1; }
+
+int cuadmm_solver_run_iterations(cuadmm_solver_t* s, int n_iters, int sgs, int profile, double out_ms[4]) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && out_ms && n_iters >= 0, "bad argument");
+        s->run_iterations(n_iters, sgs != 0, profile != 0, out_ms);
+    });
+}
+
+int cuadmm_solver_ysolve_stats(const cuadmm_solver_t* s, int64_t out[8]) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && s->ys && out, "solver not initialised");
+        if (cuadmm_ysolve_stats(s->ys, out) != 0) throw Error(CUADMM_EINVAL, cuadmm_last_error());
+    });
+}
 
 int cuadmm_solve_matlab_like(int eig_stream_num_per_gpu, int max_iter, double stop_tol, int64_t vec_len, int64_t con_num,
         const int64_t* At_jc, const int64_t* At_ir, const double* At_pr,

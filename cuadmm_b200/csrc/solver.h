@@ -66,6 +66,7 @@ struct cuadmm_solver {
               const int32_t* blk, int64_t mat_num, const double* X0, const double* y0, const double* S0, double sig);
     void solve(int max_iter, double stop_tol, int sig_update_threshold, int sig_update_stage_1,
                int sig_update_stage_2, int switch_admm, double sigscale, bool if_first);
-    void enqueue_iteration(int iter, int switch_admm);
+    void enqueue_iteration(int iter, int switch_admm, bool prof = false);
+    void run_iterations(int n_iters, bool sgs, bool profile, double out_ms[4]);
     void enqueue_half_step();
 };

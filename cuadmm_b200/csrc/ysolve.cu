@@ -25,43 +25,65 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 
 static constexpr int kTriThreads = 256;
+static constexpr int kLongRowNnz = 24;     // rows with more dependencies get a whole warp
 
-// One launch = one whole triangular sweep.  Unknowns are visited in level order (sched), G lanes
-// per unknown; every dependency x[dep] is awaited through flags[dep] (set with release semantics
-// by the group that produced it).  All CTAs are co-resident (grid sized from the occupancy API),
-// and a group only ever waits on slots that precede its own, so the sweep cannot deadlock.
-template <int G>
-__global__ void __launch_bounds__(kTriThreads) tri_sweep_kernel(
-        int64_t n_slots, const int32_t* __restrict__ sched, const int64_t* __restrict__ ptr,
+// One launch = one whole triangular sweep, level-synchronous without leaving the kernel.
+// Work is cut into warp-slots: a slot is either 8 short rows (4 lanes each) or 1 long row (32 lanes),
+// all of one dependency level.  A warp may start a slot of level l once counters[l-1] has reached the
+// number of slots of level l-1 (acquire poll by lane 0), computes its rows with ordinary coalesced
+// loads (no per-entry flag traffic), publishes x with a fence and bumps counters[l].  All CTAs are
+// co-resident (grid from the occupancy API) and every warp visits its slots in level order, so the
+// sweep cannot deadlock.
+__global__ void __launch_bounds__(kTriThreads) tri_level_kernel(
+        int64_t n_slots, const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info,
+        const int32_t* __restrict__ level_slots, const int64_t* __restrict__ ptr,
         const int32_t* __restrict__ dep, const double* __restrict__ val, const double* __restrict__ inv_diag,
         const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
-        double* x, int* flags, int64_t n_wait,
-        double* out_scatter, const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
+        double* x, int* counters, double* out_scatter, const int32_t* __restrict__ out_perm,
+        const int* __restrict__ done_flag, unsigned backoff_ns) {
     if (done_flag && *done_flag) return;
-    const int lane = threadIdx.x % G;
-    const int64_t group = ((int64_t)blockIdx.x * kTriThreads + threadIdx.x) / G;
-    const int64_t ngroups = (int64_t)gridDim.x * kTriThreads / G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-    for (int64_t s = group; s < n_slots; s += ngroups) {
-        const int32_t u = sched[s];
-        if (u < 0) continue;
-        double acc = 0.0;
-        const int64_t p1 = ptr[u + 1];
-        for (int64_t p = ptr[u] + lane; p < p1; p += G) {
-            const int32_t j = dep[p];
-            if (j < n_wait) { while (ld_acquire_gpu(flags + j) == 0) { } }
-            acc = fma(val[p], __ldcg(x + j), acc);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kTriThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kTriThreads) >> 5;
+    for (int64_t s = warp; s < n_slots; s += nwarps) {
+        const int32_t info = slot_info[s];
+        const int lvl = info & 0x3fffffff;
+        const int is_long = info >> 30;
+        if (lvl > 0) {
+            if (lane == 0) {
+                const int target = level_slots[lvl - 1];
+                while (ld_acquire_gpu(counters + lvl - 1) < target) { if (backoff_ns) __nanosleep(backoff_ns); }
+            }
+            __syncwarp();
         }
+        double acc = 0.0;
+        int32_t u;
+        if (is_long) {
+            u = slot_rows[8 * s];
+            const int64_t p1 = ptr[u + 1];
+#pragma unroll 4
+            for (int64_t p = ptr[u] + lane; p < p1; p += 32) acc = fma(val[p], __ldcg(x + dep[p]), acc);
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-        if (lane == 0) {
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        } else {
+            u = slot_rows[8 * s + (lane >> 2)];
+            if (u >= 0) {
+                const int64_t p1 = ptr[u + 1];
+                for (int64_t p = ptr[u] + (lane & 3); p < p1; p += 4) acc = fma(val[p], __ldcg(x + dep[p]), acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        }
+        const bool writer = is_long ? (lane == 0) : ((lane & 3) == 0 && u >= 0);
+        if (writer) {
             const double r = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
             const double v = (r - acc) * inv_diag[u];
             __stcg(x + u, v);
             if (out_scatter) out_scatter[out_perm[u]] = v;
             __threadfence();
-            st_release_gpu(flags + u, 1);
         }
+        __syncwarp();
+        if (lane == 0) atomicAdd(counters + lvl, 1);
     }
 }
 
@@ -87,28 +109,17 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
     }
 }
 
-static void launch_sweep(const TriSweep& S, const double* rhs, const int32_t* gather, double* x, int* flags,
-                         int64_t n_wait, double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
+static void launch_sweep(const TriSweep& S, const double* rhs, const int32_t* gather, double* x, int* counters,
+                         double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
     if (S.n_slots == 0) return;
-#define CUADMM_TRI_CASE(G)                                                                              \
-    case G:                                                                                             \
-        tri_sweep_kernel<G><<<S.grid, kTriThreads, 0, st>>>(S.n_slots, S.sched.p, S.ptr.p, S.dep.p, S.val.p, \
-            S.inv_diag.p, rhs, gather, x, flags, n_wait, out_scatter, out_perm, done);                   \
-        break;
-    switch (S.group) {
-        CUADMM_TRI_CASE(4)
-        CUADMM_TRI_CASE(8)
-        CUADMM_TRI_CASE(32)
-        default: throw Error(CUADMM_EINVAL, "bad sweep group");
-    }
-#undef CUADMM_TRI_CASE
+    tri_level_kernel<<<S.grid, kTriThreads, 0, st>>>(S.n_slots, S.slot_rows.p, S.slot_info.p, S.level_slots.p, S.ptr.p,
+        S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, counters, out_scatter, out_perm, done, S.backoff_ns);
     CUADMM_CUDA(cudaGetLastError());
 }
 
-template <int G>
 static int sweep_max_grid(int device) {
     int per_sm = 0, sms = 0;
-    CUADMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tri_sweep_kernel<G>, kTriThreads, 0));
+    CUADMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tri_level_kernel, kTriThreads, 0));
     CUADMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     return std::max(1, per_sm) * sms;
 }
@@ -126,37 +137,51 @@ struct HostSweep {
 static void upload_sweep(const HostSweep& H, TriSweep& S, int device) {
     S.n_unknowns = (int64_t)H.unknowns.size();
     S.nnz = (int64_t)H.dep.size();
-    const double avg = S.n_unknowns ? (double)S.nnz / (double)S.n_unknowns : 0.0;
-    S.group = avg >= 24.0 ? 32 : (avg >= 6.0 ? 8 : 4);
-    const int per_warp = 32 / S.group;
-    // level-ordered schedule, padded so that the slots one warp visits together share a level
-    std::vector<int32_t> order(H.unknowns);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return H.level[a] < H.level[b]; });
-    std::vector<int32_t> sched;
-    sched.reserve(order.size() + 64);
     int maxlev = -1;
-    for (size_t t = 0; t < order.size(); ++t) {
-        if (t > 0 && H.level[order[t]] != H.level[order[t - 1]])
-            while (sched.size() % per_warp) sched.push_back(-1);
-        sched.push_back(order[t]);
-        maxlev = std::max(maxlev, (int)H.level[order[t]]);
-    }
+    for (int32_t u : H.unknowns) maxlev = std::max(maxlev, (int)H.level[u]);
     S.levels = maxlev + 1;
-    S.n_slots = (int64_t)sched.size();
+    // bucket by level, short rows first (8 per warp-slot), then long rows (1 per warp-slot)
+    std::vector<std::vector<int32_t>> shorts(S.levels), longs(S.levels);
+    for (int32_t u : H.unknowns) {
+        const int64_t len = H.ptr[u + 1] - H.ptr[u];
+        (len > kLongRowNnz ? longs : shorts)[H.level[u]].push_back(u);
+    }
+    std::vector<int32_t> slot_rows, slot_info, level_slots(std::max(S.levels, 1), 0);
+    for (int l = 0; l < S.levels; ++l) {
+        int cnt = 0;
+        // heavier long rows first so the level's tail is short
+        std::stable_sort(longs[l].begin(), longs[l].end(), [&](int32_t a, int32_t b) {
+            return H.ptr[a + 1] - H.ptr[a] > H.ptr[b + 1] - H.ptr[b]; });
+        for (int32_t u : longs[l]) {
+            slot_rows.push_back(u);
+            for (int t = 1; t < 8; ++t) slot_rows.push_back(-1);
+            slot_info.push_back(l | (1 << 30));
+            ++cnt;
+        }
+        for (size_t t = 0; t < shorts[l].size(); t += 8) {
+            for (size_t q = t; q < t + 8; ++q) slot_rows.push_back(q < shorts[l].size() ? shorts[l][q] : -1);
+            slot_info.push_back(l);
+            ++cnt;
+        }
+        level_slots[l] = cnt;
+    }
+    S.n_slots = (int64_t)slot_info.size();
     S.ptr.upload(H.ptr);
     std::vector<int32_t> dep(H.dep); if (dep.empty()) dep.push_back(0);
     std::vector<double> val(H.val); if (val.empty()) val.push_back(0.0);
     S.dep.upload(dep); S.val.upload(val);
     S.inv_diag.upload(H.inv_diag);
-    if (sched.empty()) sched.push_back(-1);
-    S.sched.upload(sched);
-    int maxgrid = 1;
-    switch (S.group) {
-        case 4: maxgrid = sweep_max_grid<4>(device); break;
-        case 8: maxgrid = sweep_max_grid<8>(device); break;
-        default: maxgrid = sweep_max_grid<32>(device); break;
+    if (slot_rows.empty()) { slot_rows.assign(8, -1); slot_info.push_back(0); }
+    S.slot_rows.upload(slot_rows); S.slot_info.upload(slot_info); S.level_slots.upload(level_slots);
+    int maxgrid = sweep_max_grid(device);
+    {   // thousands of warps polling one level counter turn it into an L2 hot spot: 2 CTAs per SM measured best
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        maxgrid = std::min(maxgrid, 2 * sms);
     }
-    const int64_t need = (S.n_slots * S.group + kTriThreads - 1) / kTriThreads;
+    if (const char* e = getenv("CUADMM_SWEEP_MAXGRID")) maxgrid = std::max(1, std::min(maxgrid, atoi(e)));
+    if (const char* e = getenv("CUADMM_SWEEP_BACKOFF_NS")) S.backoff_ns = (unsigned)atoi(e);
+    const int64_t need = (S.n_slots * 32 + kTriThreads - 1) / kTriThreads;
     S.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, maxgrid));
 }
 
@@ -284,7 +309,7 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
     }
     Y->z.alloc(std::max<int64_t>(m, 1));
     Y->x.alloc(std::max<int64_t>(m, 1));
-    Y->flags.alloc(std::max<int64_t>(2 * m, 1));
+    Y->flags.alloc(std::max<int64_t>(Y->fwd.levels + Y->bwd.levels, 1));
 
     // ---- dense tail: S = M22 - L21 L21^T, Cholesky, explicit inverse (all on the device)
     if (n_tail > 0) {
@@ -305,9 +330,10 @@ using namespace cuadmm;
 
 void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st) {
     if (m == 0) return;
-    CUADMM_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * (size_t)(2 * m), st));
+    const int nl = fwd.levels + bwd.levels;
+    CUADMM_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * (size_t)std::max(nl, 1), st));
     // forward: z = L11^-1 P rhs (lead), z_tail = P rhs - L21 z_lead
-    launch_sweep(fwd, d_rhs_, perm.p, z.p, flags.p, m, nullptr, nullptr, done_flag, st);
+    launch_sweep(fwd, d_rhs_, perm.p, z.p, flags.p, nullptr, nullptr, done_flag, st);
     if (n_tail > 0) {
         const int blocks = (int)((n_tail + 7) / 8);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
@@ -316,7 +342,7 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
         CUADMM_CUDA(cudaGetLastError());
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y
-    launch_sweep(bwd, z.p, nullptr, x.p, flags.p + m, n_lead, d_y_, perm.p, done_flag, st);
+    launch_sweep(bwd, z.p, nullptr, x.p, flags.p + fwd.levels, d_y_, perm.p, done_flag, st);
 }
 
 extern "C" {

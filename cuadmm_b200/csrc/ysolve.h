@@ -17,11 +17,14 @@ struct TriSweep {
     DevBuf<int32_t> dep;
     DevBuf<double> val;
     DevBuf<double> inv_diag;
-    DevBuf<int32_t> sched;        // slots: unknown ids in level order, -1 padding
+    DevBuf<int32_t> slot_rows;    // 8 entries per warp-slot: 8 short rows, or 1 long row + padding (-1)
+    DevBuf<int32_t> slot_info;    // level | (is_long << 30)
+    DevBuf<int32_t> level_slots;  // warp-slots per level (the value counters[l] reaches when level l is done)
     int64_t n_slots = 0;
-    int group = 32;               // lanes per unknown
+    int group = 32;
     int levels = 0;
     int grid = 0;
+    unsigned backoff_ns = 100;     // sleep between polls of a not-yet-ready dependency
 };
 
 }  // namespace cuadmm
@@ -35,7 +38,7 @@ struct cuadmm_ysolve_s {
     cuadmm::DevBuf<int32_t> perm;      // perm[new] = old
     cuadmm::DevBuf<double> z;          // forward result (permuted order)
     cuadmm::DevBuf<double> x;          // backward result (permuted order)
-    cuadmm::DevBuf<int32_t> flags;     // fwd flags [0,m) + bwd flags [m, 2m)
+    cuadmm::DevBuf<int32_t> flags;     // per-level completion counters: forward levels, then backward levels
     // dense tail: inverse of the trailing Cholesky block, row-major lower and its transpose
     cuadmm::DevBuf<double> tail_inv, tail_inv_t, tail_tmp;
     cuadmm::DevBuf<double> d_rhs, d_y; // staging for the host entry

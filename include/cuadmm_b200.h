@@ -175,6 +175,14 @@ int  cuadmm_solver_history(const cuadmm_solver_t* s, int which, double* out, int
  * out[2]=solve loop, out[3]=projection total, out[4]=y-solve total, out[5]=spmv total */
 int  cuadmm_solver_times(const cuadmm_solver_t* s, double out[8]);
 int64_t cuadmm_solver_launches(const cuadmm_solver_t* s);
+/* Measurement hook: enqueue `n_iters` iterations (sGS when sgs != 0, plain ADMM otherwise) from the
+ * current state with the stop test disabled, bracketed by CUDA events on the solver's stream.
+ * out_ms[0] = total device ms; with profile != 0 also out_ms[1] = projection stage (src/solver.cu:531-675),
+ * out_ms[2] = both y-solves (:487-500,704-717), out_ms[3] = everything else (SpMVs + scalar kernel).
+ * Requires solve() to have been called once (it sets the run parameters). */
+int  cuadmm_solver_run_iterations(cuadmm_solver_t* s, int n_iters, int sgs, int profile, double out_ms[4]);
+/* y-solve statistics of the solver's factorisation (see cuadmm_ysolve_stats) */
+int  cuadmm_solver_ysolve_stats(const cuadmm_solver_t* s, int64_t out[8]);
 
 /* MEX-shaped one-shot entry: the cuadmm_MATLAB signature
  * (MATLAB/cuadmm_MATLAB.cu:197-433) over plain arrays.  At_stack is CSC

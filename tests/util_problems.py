@@ -101,49 +101,7 @@ def synthetic_sdp(blk, m, seed=0, nnz_per_con=3, hub=False):
                 xstar=xstar, pstar=float(C @ xstar))
 
 
-def chain_sdp(blk, m, seed=0, extra_frac=0.1):
-    """Moment-relaxation-like synthetic SDP (the structure of the SPOT / pendulum examples): blocks form
-    a chain (time steps); most constraints are 2-entry equalities between an svec entry of block j and
-    one of block j or j+1, a fraction `extra_frac` has 3-5 entries in blocks j, j+1; every svec entry is
-    used by at most ~2 constraints, so A A^T factors with little fill (as in the bundled examples).
-    Feasible by construction with a known optimal value."""
-    import oracle_np as onp
-    import scipy.sparse as sp
-    rng = np.random.default_rng(seed)
-    blk = np.asarray(blk, np.int32)
-    nb = len(blk)
-    off = onp.svec_offsets(blk)
-    vec_len = int(off[-1])
-    xs, ss = [], []
-    for n in blk:
-        n = int(n)
-        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
-        r = max(1, n // 3)
-        lam = np.zeros(n); lam[:r] = rng.uniform(0.5, 2.0, r)
-        mu = np.zeros(n); mu[r:] = rng.uniform(0.5, 2.0, n - r)
-        xs.append(onp.svec((Q * lam) @ Q.T)); ss.append(onp.svec((Q * mu) @ Q.T))
-    xstar, sstar = np.concatenate(xs), np.concatenate(ss)
-    # constraints are dealt to blocks proportionally to their svec length
-    w = np.diff(off).astype(float)
-    home = rng.choice(nb, size=m, p=w / w.sum())
-    home.sort()
-    k = np.where(rng.random(m) < extra_frac, rng.integers(3, 6, m), 2)
-    tot = int(k.sum())
-    con = np.repeat(np.arange(m), k)
-    hb = np.repeat(home, k)
-    nxt = np.minimum(hb + (rng.random(tot) < 0.35), nb - 1)
-    ent = off[nxt] + (rng.random(tot) * (off[nxt + 1] - off[nxt])).astype(np.int64)
-    val = rng.standard_normal(tot)
-    A = sp.csr_matrix((val, (con, ent)), shape=(m, vec_len))
-    A.sum_duplicates(); A.sort_indices()
-    b = A @ xstar
-    ystar = rng.standard_normal(m)
-    C = sstar + A.T @ ystar
-    nzb = np.nonzero(b)[0]; nzc = np.nonzero(C)[0]
-    return dict(blk=blk, vec_len=vec_len, con_num=m, col_ptrs=A.indptr.astype(np.int32),
-                row_ids=A.indices.astype(np.int32), vals=A.data.astype(np.float64),
-                b_idx=nzb.astype(np.int32), b_val=b[nzb], C_idx=nzc.astype(np.int32), C_val=C[nzc],
-                xstar=xstar, pstar=float(C @ xstar))
+from cuadmm_b200.synthetic import chain_sdp, maxcut_sdp, c2b_blocks  # noqa: E402,F401
 
 
 def make_solver(P, verbose=False, sig=1.0, X=None, y=None, S=None):
