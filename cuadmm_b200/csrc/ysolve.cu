@@ -3,10 +3,10 @@
 // Replaces the reference's per-iteration host path (src/solver.cu:487-500, 704-717):
 //   perform_permutation -> cudaDeviceSynchronize -> D2H -> cholmod_solve2 (host, simplicial LDL^T)
 //   -> H2D -> perform_permutation
-// with: gather-permute fused into a synchronisation-free sparse forward sweep, a dense GEMV pair
-// on the explicitly inverted trailing block of the factor (where the elimination DAG degenerates
-// into a chain), a sparse backward sweep with the scatter-permute fused in.  Nothing leaves the
-// GPU and there is no host synchronisation.
+// with: gather-permute fused into a level-scheduled sparse forward sweep, a dense GEMV pair on the
+// explicitly inverted trailing block of the factor (where the elimination DAG degenerates into a
+// chain), a sparse backward sweep with the scatter-permute fused in.  Nothing leaves the GPU and
+// there is no host synchronisation.
 #include "ysolve.h"
 #include "dense.h"
 #include <algorithm>
@@ -15,75 +15,97 @@
 
 namespace cuadmm {
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-    asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 static constexpr int kTriThreads = 256;
 static constexpr int kLongRowNnz = 24;     // rows with more dependencies get a whole warp
+static constexpr int kNarrowSlots = 160;   // levels with at most this many warp-slots run inside one CTA
+static constexpr int kNarrowThreads = 1024;
 
-// One launch = one whole triangular sweep, level-synchronous without leaving the kernel.
-// Work is cut into warp-slots: a slot is either 8 short rows (4 lanes each) or 1 long row (32 lanes),
-// all of one dependency level.  A warp may start a slot of level l once counters[l-1] has reached the
-// number of slots of level l-1 (acquire poll by lane 0), computes its rows with ordinary coalesced
-// loads (no per-entry flag traffic), publishes x with a fence and bumps counters[l].  All CTAs are
-// co-resident (grid from the occupancy API) and every warp visits its slots in level order, so the
-// sweep cannot deadlock.
-__global__ void __launch_bounds__(kTriThreads) tri_level_kernel(
-        int64_t n_slots, const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info,
-        const int32_t* __restrict__ level_slots, const int64_t* __restrict__ ptr,
-        const int32_t* __restrict__ dep, const double* __restrict__ val, const double* __restrict__ inv_diag,
-        const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
-        double* x, int* counters, double* out_scatter, const int32_t* __restrict__ out_perm,
-        const int* __restrict__ done_flag, unsigned backoff_ns) {
+// Work of a triangular sweep is cut into warp-slots: a slot is either 8 short rows (4 lanes each) or
+// 1 long row (32 lanes), all of one dependency level.  The levels are grouped into phases:
+//   wide level   -> one launch of tri_wide_kernel, one warp per slot, the stream order is the barrier;
+//   narrow run   -> consecutive narrow levels in ONE CTA (tri_narrow_kernel), __syncthreads between
+//                   levels (~0.1 us instead of a ~2.5 us kernel boundary or a multi-us global counter
+//                   handshake; the deep end of the elimination DAG is hundreds of levels a few rows wide).
+// No spin-waiting anywhere, so no co-residency requirement and nothing to deadlock.
+// Unknown u:  x[u] = (rhs[u] - sum_p val[p] * x[dep[p]]) * inv_diag[u].
+__device__ __forceinline__ void tri_slot(int64_t s, int lane, const int32_t* __restrict__ slot_rows, int is_long,
+        const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep, const double* __restrict__ val,
+        const double* __restrict__ inv_diag, const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
+        double* x, double* out_scatter, const int32_t* __restrict__ out_perm) {
+    double acc = 0.0;
+    int32_t u;
+    if (is_long) {
+        u = slot_rows[8 * s];
+        const int64_t p1 = ptr[u + 1];
+#pragma unroll 4
+        for (int64_t p = ptr[u] + lane; p < p1; p += 32) acc = fma(val[p], x[dep[p]], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    } else {
+        u = slot_rows[8 * s + (lane >> 2)];
+        if (u >= 0) {
+            const int64_t p1 = ptr[u + 1];
+            for (int64_t p = ptr[u] + (lane & 3); p < p1; p += 4) acc = fma(val[p], x[dep[p]], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    }
+    const bool writer = is_long ? (lane == 0) : ((lane & 3) == 0 && u >= 0);
+    if (writer) {
+        const double r = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
+        const double v = (r - acc) * inv_diag[u];
+        x[u] = v;
+        if (out_scatter) out_scatter[out_perm[u]] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kTriThreads) tri_wide_kernel(
+        int64_t slot0, int64_t slot1, const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info,
+        const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep, const double* __restrict__ val,
+        const double* __restrict__ inv_diag, const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
+        double* x, double* out_scatter, const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * kTriThreads + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * kTriThreads) >> 5;
-    for (int64_t s = warp; s < n_slots; s += nwarps) {
-        const int32_t info = slot_info[s];
-        const int lvl = info & 0x3fffffff;
-        const int is_long = info >> 30;
-        if (lvl > 0) {
-            if (lane == 0) {
-                const int target = level_slots[lvl - 1];
-                while (ld_acquire_gpu(counters + lvl - 1) < target) { if (backoff_ns) __nanosleep(backoff_ns); }
-            }
-            __syncwarp();
-        }
-        double acc = 0.0;
-        int32_t u;
-        if (is_long) {
-            u = slot_rows[8 * s];
-            const int64_t p1 = ptr[u + 1];
-#pragma unroll 4
-            for (int64_t p = ptr[u] + lane; p < p1; p += 32) acc = fma(val[p], __ldcg(x + dep[p]), acc);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        } else {
-            u = slot_rows[8 * s + (lane >> 2)];
-            if (u >= 0) {
-                const int64_t p1 = ptr[u + 1];
-                for (int64_t p = ptr[u] + (lane & 3); p < p1; p += 4) acc = fma(val[p], __ldcg(x + dep[p]), acc);
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        }
-        const bool writer = is_long ? (lane == 0) : ((lane & 3) == 0 && u >= 0);
-        if (writer) {
-            const double r = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
-            const double v = (r - acc) * inv_diag[u];
-            __stcg(x + u, v);
-            if (out_scatter) out_scatter[out_perm[u]] = v;
-            __threadfence();
-        }
-        __syncwarp();
-        if (lane == 0) atomicAdd(counters + lvl, 1);
+    const int64_t s = slot0 + (((int64_t)blockIdx.x * kTriThreads + threadIdx.x) >> 5);
+    if (s >= slot1) return;
+    tri_slot(s, lane, slot_rows, slot_info[s] >> 30, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm);
+}
+
+__global__ void __launch_bounds__(kNarrowThreads) tri_narrow_kernel(
+        int level0, int level1, const int64_t* __restrict__ level_ptr, const int32_t* __restrict__ slot_rows,
+        const int32_t* __restrict__ slot_info, const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep,
+        const double* __restrict__ val, const double* __restrict__ inv_diag, const double* __restrict__ rhs,
+        const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter, const int32_t* __restrict__ out_perm,
+        const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int l = level0; l < level1; ++l) {
+        const int64_t s1 = level_ptr[l + 1];
+        for (int64_t s = level_ptr[l] + warp; s < s1; s += kNarrowThreads / 32)
+            tri_slot(s, lane, slot_rows, slot_info[s] >> 30, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm);
+        __syncthreads();   // also makes this CTA's global writes visible to its own later loads
+    }
+}
+
+// Subtree parallelism: every CTA owns one subtree of the elimination tree (all of whose dependencies
+// are inside the subtree, or already final), and walks the subtree's own levels with __syncthreads.
+// Thousands of independent deep chains (one per block neighbourhood of a moment relaxation) thus cost
+// ONE launch and depth x ~0.3 us instead of depth x (kernel boundary).
+__global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(
+        const int64_t* __restrict__ sub_off, const int64_t* __restrict__ sub_lvl_ptr,
+        const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info,
+        const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep, const double* __restrict__ val,
+        const double* __restrict__ inv_diag, const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
+        double* x, double* out_scatter, const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = sub_off[blockIdx.x];
+    const int nl = (int)(sub_off[blockIdx.x + 1] - base) - 1;
+    for (int l = 0; l < nl; ++l) {
+        const int64_t s1 = sub_lvl_ptr[base + l + 1];
+        for (int64_t s = sub_lvl_ptr[base + l] + warp; s < s1; s += kTriThreads / 32)
+            tri_slot(s, lane, slot_rows, slot_info[s] >> 30, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm);
+        __syncthreads();
     }
 }
 
@@ -109,19 +131,32 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
     }
 }
 
-static void launch_sweep(const TriSweep& S, const double* rhs, const int32_t* gather, double* x, int* counters,
-                         double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
-    if (S.n_slots == 0) return;
-    tri_level_kernel<<<S.grid, kTriThreads, 0, st>>>(S.n_slots, S.slot_rows.p, S.slot_info.p, S.level_slots.p, S.ptr.p,
-        S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, counters, out_scatter, out_perm, done, S.backoff_ns);
-    CUADMM_CUDA(cudaGetLastError());
+static void launch_subtrees(const TriSweep& S, const double* rhs, const int32_t* gather, double* x,
+                            double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
+    if (S.n_sub == 0) return;
+    tri_subtree_kernel<<<(unsigned)S.n_sub, kTriThreads, 0, st>>>(S.sub_off.p, S.sub_lvl_ptr.p, S.slot_rows.p, S.slot_info.p,
+        S.ptr.p, S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
 }
 
-static int sweep_max_grid(int device) {
-    int per_sm = 0, sms = 0;
-    CUADMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tri_level_kernel, kTriThreads, 0));
-    CUADMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    return std::max(1, per_sm) * sms;
+static int launch_sweep(const TriSweep& S, const double* rhs, const int32_t* gather, double* x,
+                        double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
+    int launches = 0;
+    if (S.subtrees_first && S.n_sub) { launch_subtrees(S, rhs, gather, x, out_scatter, out_perm, done, st); ++launches; }
+    for (const TriSweep::Phase& ph : S.phases) {
+        if (ph.narrow) {
+            tri_narrow_kernel<<<1, kNarrowThreads, 0, st>>>(ph.level0, ph.level1, S.level_ptr.p, S.slot_rows.p, S.slot_info.p,
+                S.ptr.p, S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
+        } else {
+            const int64_t s0 = S.h_level_ptr[ph.level0], s1 = S.h_level_ptr[ph.level1];
+            const int grid = (int)(((s1 - s0) * 32 + kTriThreads - 1) / kTriThreads);
+            tri_wide_kernel<<<grid, kTriThreads, 0, st>>>(s0, s1, S.slot_rows.p, S.slot_info.p, S.ptr.p, S.dep.p, S.val.p,
+                S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
+        }
+        ++launches;
+    }
+    if (!S.subtrees_first && S.n_sub) { launch_subtrees(S, rhs, gather, x, out_scatter, out_perm, done, st); ++launches; }
+    CUADMM_CUDA(cudaGetLastError());
+    return launches;
 }
 
 // host: pull structure -> device sweep
@@ -129,60 +164,138 @@ struct HostSweep {
     std::vector<int64_t> ptr;
     std::vector<int32_t> dep;
     std::vector<double> val, inv_diag;
-    std::vector<int32_t> level;   // per unknown
-    int64_t n = 0;                // unknown id space
-    std::vector<int32_t> unknowns;  // ids actually solved by the sweep
+    int64_t n = 0;                  // unknown id space
+    std::vector<int32_t> order;     // the unknowns of this sweep in a valid (topological) solve order
+    std::vector<int32_t> sub;       // per unknown id: subtree id, or -1 = top part
+    int64_t n_sub = 0;
+    bool subtrees_first = true;     // forward: subtrees then top; backward: top then subtrees
 };
 
-static void upload_sweep(const HostSweep& H, TriSweep& S, int device) {
-    S.n_unknowns = (int64_t)H.unknowns.size();
-    S.nnz = (int64_t)H.dep.size();
-    int maxlev = -1;
-    for (int32_t u : H.unknowns) maxlev = std::max(maxlev, (int)H.level[u]);
-    S.levels = maxlev + 1;
-    // bucket by level, short rows first (8 per warp-slot), then long rows (1 per warp-slot)
-    std::vector<std::vector<int32_t>> shorts(S.levels), longs(S.levels);
-    for (int32_t u : H.unknowns) {
-        const int64_t len = H.ptr[u + 1] - H.ptr[u];
-        (len > kLongRowNnz ? longs : shorts)[H.level[u]].push_back(u);
+// slots for a list of unknowns that all belong to one level
+static int64_t emit_level_slots(const HostSweep& H, std::vector<int32_t>& rows, int level,
+                                std::vector<int32_t>& slot_rows, std::vector<int32_t>& slot_info) {
+    std::vector<int32_t> longs, shorts;
+    for (int32_t u : rows) ((H.ptr[u + 1] - H.ptr[u]) > kLongRowNnz ? longs : shorts).push_back(u);
+    std::stable_sort(longs.begin(), longs.end(), [&](int32_t a, int32_t b) {
+        return H.ptr[a + 1] - H.ptr[a] > H.ptr[b + 1] - H.ptr[b]; });
+    int64_t cnt = 0;
+    for (int32_t u : longs) {
+        slot_rows.push_back(u);
+        for (int t = 1; t < 8; ++t) slot_rows.push_back(-1);
+        slot_info.push_back(level | (1 << 30));
+        ++cnt;
     }
-    std::vector<int32_t> slot_rows, slot_info, level_slots(std::max(S.levels, 1), 0);
+    for (size_t t = 0; t < shorts.size(); t += 8) {
+        for (size_t q = t; q < t + 8; ++q) slot_rows.push_back(q < shorts.size() ? shorts[q] : -1);
+        slot_info.push_back(level);
+        ++cnt;
+    }
+    return cnt;
+}
+
+static void upload_sweep(const HostSweep& H, TriSweep& S) {
+    S.n_unknowns = (int64_t)H.order.size();
+    S.nnz = (int64_t)H.dep.size();
+    S.subtrees_first = H.subtrees_first;
+    // levels inside each part (a subtree, or the top): dependencies that live in another part are
+    // final by construction of the launch order and do not count
+    std::vector<int32_t> level(H.n, 0);
+    for (int32_t u : H.order) {
+        int32_t l = 0;
+        for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) {
+            const int32_t d = H.dep[p];
+            if (H.sub[d] == H.sub[u]) l = std::max(l, level[d] + 1);
+        }
+        level[u] = l;
+    }
+    std::vector<int32_t> slot_rows, slot_info;
+    // ---- subtree part: slots grouped by (subtree, level); deepest subtrees first
+    std::vector<std::vector<int32_t>> members(H.n_sub);
+    std::vector<int32_t> depth(H.n_sub, 0);
+    for (int32_t u : H.order) if (H.sub[u] >= 0) {
+        members[H.sub[u]].push_back(u);
+        depth[H.sub[u]] = std::max(depth[H.sub[u]], level[u] + 1);
+    }
+    std::vector<int32_t> sub_order(H.n_sub);
+    std::iota(sub_order.begin(), sub_order.end(), 0);
+    std::stable_sort(sub_order.begin(), sub_order.end(), [&](int32_t a, int32_t b) { return depth[a] > depth[b]; });
+    std::vector<int64_t> sub_off(1, 0), sub_lvl_ptr;
+    int max_sub_depth = 0;
+    for (int32_t t : sub_order) {
+        std::vector<std::vector<int32_t>> by_level(depth[t]);
+        for (int32_t u : members[t]) by_level[level[u]].push_back(u);
+        for (int l = 0; l < depth[t]; ++l) {
+            sub_lvl_ptr.push_back((int64_t)slot_info.size());
+            emit_level_slots(H, by_level[l], l, slot_rows, slot_info);
+        }
+        sub_lvl_ptr.push_back((int64_t)slot_info.size());
+        sub_off.push_back((int64_t)sub_lvl_ptr.size());
+        max_sub_depth = std::max(max_sub_depth, depth[t]);
+    }
+    S.n_sub = H.n_sub;
+    S.sub_depth = max_sub_depth;
+    // ---- top part: global levels, wide levels one launch each, narrow runs in one CTA
+    int maxlev = -1;
+    for (int32_t u : H.order) if (H.sub[u] < 0) maxlev = std::max(maxlev, (int)level[u]);
+    S.levels = maxlev + 1;
+    std::vector<std::vector<int32_t>> top_by_level(std::max(S.levels, 0));
+    for (int32_t u : H.order) if (H.sub[u] < 0) top_by_level[level[u]].push_back(u);
+    S.h_level_ptr.assign(S.levels + 1, (int64_t)slot_info.size());
+    std::vector<int64_t> level_slots(std::max(S.levels, 1), 0);
     for (int l = 0; l < S.levels; ++l) {
-        int cnt = 0;
-        // heavier long rows first so the level's tail is short
-        std::stable_sort(longs[l].begin(), longs[l].end(), [&](int32_t a, int32_t b) {
-            return H.ptr[a + 1] - H.ptr[a] > H.ptr[b + 1] - H.ptr[b]; });
-        for (int32_t u : longs[l]) {
-            slot_rows.push_back(u);
-            for (int t = 1; t < 8; ++t) slot_rows.push_back(-1);
-            slot_info.push_back(l | (1 << 30));
-            ++cnt;
-        }
-        for (size_t t = 0; t < shorts[l].size(); t += 8) {
-            for (size_t q = t; q < t + 8; ++q) slot_rows.push_back(q < shorts[l].size() ? shorts[l][q] : -1);
-            slot_info.push_back(l);
-            ++cnt;
-        }
-        level_slots[l] = cnt;
+        S.h_level_ptr[l] = (int64_t)slot_info.size();
+        level_slots[l] = emit_level_slots(H, top_by_level[l], l, slot_rows, slot_info);
+        S.h_level_ptr[l + 1] = (int64_t)slot_info.size();
     }
     S.n_slots = (int64_t)slot_info.size();
+    int narrow_slots = kNarrowSlots;
+    if (const char* e = getenv("CUADMM_SWEEP_NARROW_SLOTS")) narrow_slots = atoi(e);
+    S.phases.clear();
+    for (int l = 0; l < S.levels;) {
+        if (level_slots[l] <= narrow_slots) {
+            int e = l;
+            while (e < S.levels && level_slots[e] <= narrow_slots) ++e;
+            S.phases.push_back({true, l, e});
+            l = e;
+        } else {
+            S.phases.push_back({false, l, l + 1});
+            ++l;
+        }
+    }
     S.ptr.upload(H.ptr);
     std::vector<int32_t> dep(H.dep); if (dep.empty()) dep.push_back(0);
     std::vector<double> val(H.val); if (val.empty()) val.push_back(0.0);
     S.dep.upload(dep); S.val.upload(val);
     S.inv_diag.upload(H.inv_diag);
     if (slot_rows.empty()) { slot_rows.assign(8, -1); slot_info.push_back(0); }
-    S.slot_rows.upload(slot_rows); S.slot_info.upload(slot_info); S.level_slots.upload(level_slots);
-    int maxgrid = sweep_max_grid(device);
-    {   // thousands of warps polling one level counter turn it into an L2 hot spot: 2 CTAs per SM measured best
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        maxgrid = std::min(maxgrid, 2 * sms);
+    S.slot_rows.upload(slot_rows); S.slot_info.upload(slot_info);
+    S.level_ptr.upload(S.h_level_ptr);
+    if (sub_lvl_ptr.empty()) sub_lvl_ptr.push_back(0);
+    S.sub_off.upload(sub_off); S.sub_lvl_ptr.upload(sub_lvl_ptr);
+}
+
+// Disjoint subtrees of the elimination tree (lead part only), each at most `cap` rows: v roots a
+// subtree when its own subtree fits and its parent's does not (or the parent is in the dense tail).
+static int64_t choose_subtrees(const CholFactor& F, int64_t n_lead, std::vector<int32_t>& sub) {
+    const int64_t n = F.n;
+    sub.assign(n, -1);
+    int64_t cap = 8192;
+    if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_CAP")) cap = atoll(e);
+    if (cap <= 0) return 0;
+    std::vector<int64_t> size(n, 1);
+    for (int64_t v = 0; v < n_lead; ++v) {
+        const int32_t p = F.parent[v];
+        if (p >= 0 && p < n_lead) size[p] += size[v];
     }
-    if (const char* e = getenv("CUADMM_SWEEP_MAXGRID")) maxgrid = std::max(1, std::min(maxgrid, atoi(e)));
-    if (const char* e = getenv("CUADMM_SWEEP_BACKOFF_NS")) S.backoff_ns = (unsigned)atoi(e);
-    const int64_t need = (S.n_slots * 32 + kTriThreads - 1) / kTriThreads;
-    S.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, maxgrid));
+    int64_t n_sub = 0;
+    for (int64_t v = n_lead - 1; v >= 0; --v) {
+        const int32_t p = F.parent[v];
+        const bool parent_top = (p < 0 || p >= n_lead || sub[p] < 0);
+        if (!parent_top) { sub[v] = sub[p]; continue; }
+        const bool parent_fits = (p >= 0 && p < n_lead && size[p] <= cap);
+        if (size[v] <= cap && !parent_fits && size[v] >= 2) sub[v] = (int32_t)n_sub++;
+    }
+    return n_sub;
 }
 
 // choose the rows that go to the dense tail: the deep, narrow end of the elimination DAG.
@@ -246,7 +359,6 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         F = CholFactor();
         chol_symbolic(M, perm1, F, &C);
     } else {
-        std::vector<int32_t> ip;
         chol_symbolic(M, perm0, F, &C);
     }
     chol_numeric(C, F, n_lead);
@@ -256,6 +368,8 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
     Y->h_perm = F.perm;
     Y->perm.upload(F.perm);
 
+    std::vector<int32_t> sub;
+    const int64_t n_sub = choose_subtrees(F, n_lead, sub);
     // ---- forward sweep: rows of L (lead rows solve, tail rows accumulate t2 = b2 - L21 z1)
     {
         HostSweep H;
@@ -273,15 +387,10 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
             }
         H.inv_diag.assign(m, 1.0);
         for (int64_t i = 0; i < n_lead; ++i) H.inv_diag[i] = 1.0 / F.Lx[F.Lp[i]];
-        H.level.assign(m, 0);
-        for (int64_t i = 0; i < m; ++i) {
-            int32_t l = 0;
-            for (int64_t p = H.ptr[i]; p < H.ptr[i + 1]; ++p) l = std::max(l, H.level[H.dep[p]] + 1);
-            H.level[i] = l;
-        }
-        H.unknowns.resize(m);
-        std::iota(H.unknowns.begin(), H.unknowns.end(), 0);
-        upload_sweep(H, Y->fwd, device);
+        H.order.resize(m);
+        std::iota(H.order.begin(), H.order.end(), 0);
+        H.sub = sub; H.n_sub = n_sub; H.subtrees_first = true;
+        upload_sweep(H, Y->fwd);
     }
     // ---- backward sweep: columns of L as rows of L^T, lead unknowns only
     {
@@ -297,19 +406,16 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         }
         H.inv_diag.assign(m, 1.0);
         for (int64_t i = 0; i < n_lead; ++i) H.inv_diag[i] = 1.0 / F.Lx[F.Lp[i]];
-        H.level.assign(m, 0);
-        for (int64_t j = n_lead - 1; j >= 0; --j) {
-            int32_t l = 0;
-            for (int64_t p = H.ptr[j]; p < H.ptr[j + 1]; ++p) if (H.dep[p] < n_lead) l = std::max(l, H.level[H.dep[p]] + 1);
-            H.level[j] = l;
-        }
-        H.unknowns.resize(n_lead);
-        std::iota(H.unknowns.begin(), H.unknowns.end(), 0);
-        upload_sweep(H, Y->bwd, device);
+        H.order.resize(n_lead);
+        for (int64_t j = 0; j < n_lead; ++j) H.order[j] = (int32_t)(n_lead - 1 - j);
+        // tail unknowns are final before the backward sweep starts: give them their own "part"
+        H.sub = sub;
+        for (int64_t i = n_lead; i < m; ++i) H.sub[i] = -2;
+        H.n_sub = n_sub; H.subtrees_first = false;
+        upload_sweep(H, Y->bwd);
     }
     Y->z.alloc(std::max<int64_t>(m, 1));
     Y->x.alloc(std::max<int64_t>(m, 1));
-    Y->flags.alloc(std::max<int64_t>(Y->fwd.levels + Y->bwd.levels, 1));
 
     // ---- dense tail: S = M22 - L21 L21^T, Cholesky, explicit inverse (all on the device)
     if (n_tail > 0) {
@@ -318,7 +424,7 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         Y->n_deficient += tail_def;
         Y->tail_tmp.alloc(n_tail);
     }
-    Y->launches_per_solve = 1 + 2 + (n_tail > 0 ? 2 : 0);
+    Y->launches_per_solve = (int)(Y->fwd.phases.size() + Y->bwd.phases.size()) + (n_tail > 0 ? 2 : 0) + (n_sub > 0 ? 2 : 0);
     Y->alg_bytes = 2 * (12 * Y->nnz_L + 8 * m) + 24 * m;
     CUADMM_CUDA(cudaDeviceSynchronize());
     return Y.release();
@@ -330,10 +436,8 @@ using namespace cuadmm;
 
 void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st) {
     if (m == 0) return;
-    const int nl = fwd.levels + bwd.levels;
-    CUADMM_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * (size_t)std::max(nl, 1), st));
     // forward: z = L11^-1 P rhs (lead), z_tail = P rhs - L21 z_lead
-    launch_sweep(fwd, d_rhs_, perm.p, z.p, flags.p, nullptr, nullptr, done_flag, st);
+    launch_sweep(fwd, d_rhs_, perm.p, z.p, nullptr, nullptr, done_flag, st);
     if (n_tail > 0) {
         const int blocks = (int)((n_tail + 7) / 8);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
@@ -342,7 +446,7 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
         CUADMM_CUDA(cudaGetLastError());
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y
-    launch_sweep(bwd, z.p, nullptr, x.p, flags.p + fwd.levels, d_y_, perm.p, done_flag, st);
+    launch_sweep(bwd, z.p, nullptr, x.p, d_y_, perm.p, done_flag, st);
 }
 
 extern "C" {
@@ -383,7 +487,7 @@ int cuadmm_ysolve_stats(const cuadmm_ysolve_t* ys, int64_t out[8]) {
         CUADMM_REQUIRE(ys && out, "null argument");
         out[0] = ys->nnz_aat; out[1] = ys->nnz_L; out[2] = std::max(ys->fwd.levels, ys->bwd.levels);
         out[3] = ys->n_tail; out[4] = ys->launches_per_solve; out[5] = ys->alg_bytes;
-        out[6] = ys->n_deficient; out[7] = ys->fwd.grid;
+        out[6] = ys->n_deficient; out[7] = ys->fwd.n_sub * 100000 + ys->fwd.sub_depth;
     });
 }
 

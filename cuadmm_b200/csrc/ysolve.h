@@ -5,11 +5,10 @@
 
 namespace cuadmm {
 
-// One pull-style sparse triangular sweep: unknown u (processed in `sched` order) is
+// One pull-style sparse triangular sweep: unknown u is
 //   x[u] = (rhs[u] - sum_p val[p] * x[dep[p]]) * inv_diag[u]
 // Forward solve with L: u = row, deps = columns < u.  Backward solve with L^T: u = column,
-// deps = rows > u.  Same kernel for both; dependencies are awaited through per-unknown flags
-// (synchronisation-free SpTRSV), so one launch covers the whole dependency DAG.
+// deps = rows > u.  Same kernels for both (see ysolve.cu for the level/phase scheme).
 struct TriSweep {
     int64_t n_unknowns = 0;       // unknowns solved by this sweep
     int64_t nnz = 0;
@@ -19,12 +18,17 @@ struct TriSweep {
     DevBuf<double> inv_diag;
     DevBuf<int32_t> slot_rows;    // 8 entries per warp-slot: 8 short rows, or 1 long row + padding (-1)
     DevBuf<int32_t> slot_info;    // level | (is_long << 30)
-    DevBuf<int32_t> level_slots;  // warp-slots per level (the value counters[l] reaches when level l is done)
+    DevBuf<int64_t> level_ptr;    // first slot of every level (levels+1)
+    std::vector<int64_t> h_level_ptr;
+    struct Phase { bool narrow; int level0, level1; };
+    std::vector<Phase> phases;    // launch plan: wide levels one by one, runs of narrow levels in one CTA
     int64_t n_slots = 0;
-    int group = 32;
-    int levels = 0;
-    int grid = 0;
-    unsigned backoff_ns = 100;     // sleep between polls of a not-yet-ready dependency
+    int levels = 0;               // levels of the top part
+    // subtree part: CTA t walks levels [sub_off[t], sub_off[t+1]-1) of sub_lvl_ptr (slot offsets)
+    DevBuf<int64_t> sub_off, sub_lvl_ptr;
+    int64_t n_sub = 0;
+    int sub_depth = 0;
+    bool subtrees_first = true;
 };
 
 }  // namespace cuadmm
@@ -38,7 +42,6 @@ struct cuadmm_ysolve_s {
     cuadmm::DevBuf<int32_t> perm;      // perm[new] = old
     cuadmm::DevBuf<double> z;          // forward result (permuted order)
     cuadmm::DevBuf<double> x;          // backward result (permuted order)
-    cuadmm::DevBuf<int32_t> flags;     // per-level completion counters: forward levels, then backward levels
     // dense tail: inverse of the trailing Cholesky block, row-major lower and its transpose
     cuadmm::DevBuf<double> tail_inv, tail_inv_t, tail_tmp;
     cuadmm::DevBuf<double> d_rhs, d_y; // staging for the host entry
