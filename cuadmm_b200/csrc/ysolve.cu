@@ -279,7 +279,7 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
 static int64_t choose_subtrees(const CholFactor& F, int64_t n_lead, std::vector<int32_t>& sub) {
     const int64_t n = F.n;
     sub.assign(n, -1);
-    int64_t cap = 8192;
+    int64_t cap = 32768;
     if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_CAP")) cap = atoll(e);
     if (cap <= 0) return 0;
     std::vector<int64_t> size(n, 1);
@@ -307,7 +307,7 @@ static int64_t choose_tail(const CholFactor& F, std::vector<int32_t>& level_out)
     level_out = lev;
     int depth = 0;
     for (int64_t i = 0; i < n; ++i) depth = std::max(depth, lev[i] + 1);
-    int64_t max_tail = 6144;
+    int64_t max_tail = 10240;
     int min_depth = 64;
     if (const char* e = getenv("CUADMM_YSOLVE_MAX_TAIL")) max_tail = atoll(e);
     if (const char* e = getenv("CUADMM_YSOLVE_MIN_DEPTH")) min_depth = atoi(e);
