@@ -172,6 +172,8 @@ cuadmm_solver::~cuadmm_solver() {
     if (ev_start) cudaEventDestroy(ev_start);
     if (ev_now) cudaEventDestroy(ev_now);
     for (auto e : prof_ev) cudaEventDestroy(e);
+    if (graph_sgs) cudaGraphExecDestroy(graph_sgs);
+    if (graph_admm) cudaGraphExecDestroy(graph_admm);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -190,6 +192,7 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
         throw Error(CUADMM_ENODEVICE, "no CUDA device available; the solver has no CPU fallback");
     }
     if (const char* e = getenv("CUADMM_DEVICE")) device = atoi(e);
+    if (const char* e = getenv("CUADMM_NO_GRAPH")) use_graphs = atoi(e) == 0;
     CUADMM_REQUIRE(device >= 0 && device < cnt, "device index out of range");
     CUADMM_CUDA(cudaSetDevice(device));
     vec_len = vec_len_; con_num = con_num_;
@@ -371,6 +374,35 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
     CUADMM_CUDA(cudaGetLastError());
 }
 
+// One iteration = one CUDA-graph launch (the kernel sequence does not depend on the iteration index
+// except at iter == switch_admm, which is enqueued directly).  Launch-bound problems (ros_2000: ~15
+// kernels of a few microseconds each) otherwise spend more time in the driver than on the GPU.
+void cuadmm_solver::launch_iteration(int iter, int switch_admm, bool prof) {
+    if (prof || !use_graphs || iter == switch_admm) { enqueue_iteration(iter, switch_admm, prof); return; }
+    const bool sgs = iter < switch_admm;
+    cudaGraphExec_t& exec = sgs ? graph_sgs : graph_admm;
+    int64_t& nl = sgs ? graph_launches_sgs : graph_launches_admm;
+    if (!exec) {
+        const int64_t before = launches;
+        cudaGraph_t graph = nullptr;
+        CUADMM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue_iteration(iter, switch_admm, false);
+        } catch (...) {
+            cudaStreamEndCapture(stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        CUADMM_CUDA(cudaStreamEndCapture(stream, &graph));
+        CUADMM_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        CUADMM_CUDA(cudaGraphDestroy(graph));
+        nl = launches - before;
+        launches = before;
+    }
+    CUADMM_CUDA(cudaGraphLaunch(exec, stream));
+    launches += nl;
+}
+
 // what the reference still executes at the top of the iteration in which it breaks
 // (step 1 and step 2a, src/solver.cu:478-528): y is overwritten by the next half-step.
 void cuadmm_solver::enqueue_half_step() {
@@ -401,7 +433,7 @@ void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double 
     cudaEvent_t e0, e1;
     CUADMM_CUDA(cudaEventCreate(&e0)); CUADMM_CUDA(cudaEventCreate(&e1));
     CUADMM_CUDA(cudaEventRecord(e0, stream));
-    for (int k = 0; k < n_iters; ++k) enqueue_iteration(first + k, sw, profile_);
+    for (int k = 0; k < n_iters; ++k) launch_iteration(first + k, sw, profile_);
     CUADMM_CUDA(cudaEventRecord(e1, stream));
     CUADMM_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
@@ -437,12 +469,15 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     const auto t0 = std::chrono::steady_clock::now();
     const int64_t n = vec_len, m = con_num;
     const int gv = ew_grid(n, device), gm = ew_grid(m, device);
-    if (switch_admm <= max_iter + 1 && X_best.n < std::max<int64_t>(n, 1)) {
+    if (X_best.n < std::max<int64_t>(n, 1)) {   // always allocated: the ADMM graph bakes these pointers
         X_best.alloc(std::max<int64_t>(n, 1)); y_best.alloc(std::max<int64_t>(m, 1)); S_best.alloc(std::max<int64_t>(n, 1));
     }
     if ((int64_t)max_iter + 1 > hist_cap || hist.n == 0) {   // keep the buffer across warm-restart calls
         hist_cap = (int64_t)max_iter + 1;
         hist.alloc(8 * hist_cap);
+        // the captured graphs bake the history pointer
+        if (graph_sgs) { cudaGraphExecDestroy(graph_sgs); graph_sgs = nullptr; }
+        if (graph_admm) { cudaGraphExecDestroy(graph_admm); graph_admm = nullptr; }
     }
     info_iter_num = 0;
 
@@ -503,7 +538,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
         if (done) { stop_iter = cur; break; }
         int target = it + 1;
         while (!is_log_iter(target) && target <= max_iter) ++target;
-        for (int k = it; k < target; ++k) enqueue_iteration(k, switch_admm);
+        for (int k = it; k < target; ++k) launch_iteration(k, switch_admm, false);
         it = target;
     }
     info_iter_num = stop_iter - 1;

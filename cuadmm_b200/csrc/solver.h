@@ -69,4 +69,9 @@ struct cuadmm_solver {
     void enqueue_iteration(int iter, int switch_admm, bool prof = false);
     void run_iterations(int n_iters, bool sgs, bool profile, double out_ms[4]);
     void enqueue_half_step();
+    // whole-iteration CUDA graphs (one for the sGS iteration, one for the plain ADMM iteration)
+    cudaGraphExec_t graph_sgs = nullptr, graph_admm = nullptr;
+    int64_t graph_launches_sgs = 0, graph_launches_admm = 0;
+    bool use_graphs = true;
+    void launch_iteration(int iter, int switch_admm, bool prof);
 };
