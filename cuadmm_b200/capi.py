@@ -316,7 +316,59 @@ _maybe("cuadmm_solver_times", C.c_int, vp, c_f64p)
 _maybe("cuadmm_solver_launches", C.c_int64, vp)
 _maybe("cuadmm_solver_run_iterations", C.c_int, vp, C.c_int, C.c_int, C.c_int, c_f64p)
 _maybe("cuadmm_solver_ysolve_stats", C.c_int, vp, c_i64p)
+_maybe("cuadmm_nccl_unique_id", C.c_int, C.c_char_p)
+_maybe("cuadmm_solver_set_distributed", C.c_int, vp, C.c_int, C.c_int, C.c_char_p)
+_maybe("cuadmm_shard_create", C.c_int, c_i32p, C.c_int64, C.c_int, C.c_int, C.POINTER(vp))
+_maybe("cuadmm_shard_destroy", None, vp)
+_maybe("cuadmm_shard_info", C.c_int, vp, c_i64p)
+_maybe("cuadmm_shard_maps", C.c_int, vp, c_i32p, c_i64p, c_i64p, c_i32p)
+_maybe("cuadmm_shard_slice_csc", C.c_int64, vp, C.c_int64, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p)
 _maybe("cuadmm_solver_init_from_problem", C.c_int, vp, vp, C.c_int, C.c_int, C.c_double)
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib.cuadmm_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Shard:
+    """Block-level sharding of an SDP over `world` GPUs (cuadmm_shard_*; host logic only)."""
+
+    def __init__(self, blk, world, rank):
+        self.blk = _i32(blk)
+        self.h = vp()
+        _check(lib.cuadmm_shard_create(_p(self.blk, c_i32p), len(self.blk), world, rank, C.byref(self.h)))
+        info = np.zeros(4, np.int64)
+        _check(lib.cuadmm_shard_info(self.h, _p(info, c_i64p)))
+        self.vec_len_local, self.nblk_local, self.vec_len, self.world = [int(x) for x in info]
+        self.local_blk = np.zeros(self.nblk_local, np.int32)
+        self.local_block_ids = np.zeros(self.nblk_local, np.int64)
+        self.loc2glob = np.zeros(self.vec_len_local, np.int64)
+        self.owner = np.zeros(len(self.blk), np.int32)
+        _check(lib.cuadmm_shard_maps(self.h, _p(self.local_blk, c_i32p), _p(self.local_block_ids, c_i64p),
+                                     _p(self.loc2glob, c_i64p), _p(self.owner, c_i32p)))
+
+    def slice_csc(self, col_ptrs, row_ids, vals):
+        col_ptrs, row_ids, vals = _i32(col_ptrs), _i32(row_ids), _f64(vals)
+        ncols = len(col_ptrs) - 1
+        ocp = np.zeros(ncols + 1, np.int32); ori = np.zeros(max(len(vals), 1), np.int32); ov = np.zeros(max(len(vals), 1))
+        nnz = lib.cuadmm_shard_slice_csc(self.h, ncols, _p(col_ptrs, c_i32p), _p(row_ids, c_i32p), _p(vals, c_f64p),
+                                         _p(ocp, c_i32p), _p(ori, c_i32p), _p(ov, c_f64p))
+        if nnz < 0:
+            raise CuadmmError(-1, lib.cuadmm_last_error().decode())
+        return ocp, ori[:nnz], ov[:nnz]
+
+    def close(self):
+        if self.h:
+            lib.cuadmm_shard_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Problem:
@@ -376,6 +428,10 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+    def set_distributed(self, rank, world, nccl_id):
+        """one process per GPU: call before init with the id rank 0 got from nccl_unique_id()"""
+        _check(lib.cuadmm_solver_set_distributed(self.h, int(rank), int(world), nccl_id))
 
     def init(self, eig_stream_num_per_gpu, cpu_eig_thread_num, vec_len, con_num,
              At_csc_col_ptrs, At_csc_row_ids, At_csc_vals, b_indices, b_vals, C_indices, C_vals, blk_vals,

@@ -142,6 +142,53 @@ __global__ void sub_kernel(int64_t n, const double* __restrict__ a, const double
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
 }
 
+// distributed K1: rhsy = Rp / sig + buf   (buf = all-reduced  -A (S-C))
+__global__ void rhsy_kernel(int64_t m, const double* __restrict__ Rp, const double* __restrict__ buf, double* rhsy, const DevState* st) {
+    if (st->done) return;
+    const double sig = st->sig;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) rhsy[i] = Rp[i] / sig + buf[i];
+}
+// local per-CTA partial pairs -> two scalars appended to the all-reduce buffer
+__global__ void __launch_bounds__(256) fold_partials_kernel(const double* __restrict__ part, int n, double* out2, const DevState* st) {
+    if (st->done) return;
+    __shared__ double sm[2][256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { a += part[2 * i]; b += part[2 * i + 1]; }
+    sm[0][threadIdx.x] = a; sm[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sm[0][threadIdx.x] += sm[0][threadIdx.x + o]; sm[1][threadIdx.x] += sm[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = sm[0][0]; out2[1] = sm[1][0]; }
+}
+// distributed K8: Rp = b - buf (buf = all-reduced A X) ; partial sums |normA Rp|^2, <b, y>
+__global__ void __launch_bounds__(kEwThreads) rp_kernel(int64_t m, const double* __restrict__ b, const double* __restrict__ buf,
+        const double* __restrict__ normA, const double* __restrict__ y, double* Rp, const DevState* st, double* partial) {
+    if (st->done) return;
+    __shared__ double red[2][kEwThreads / 32];
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < m; i += (int64_t)gridDim.x * kEwThreads) {
+        const double rp = b[i] - buf[i];
+        Rp[i] = rp;
+        const double t = normA[i] * rp;
+        a0 = fma(t, t, a0);
+        a1 = fma(b[i], y[i], a1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < kEwThreads / 32; ++k) { s0 += red[0][k]; s1 += red[1][k]; }
+        partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1;
+    }
+}
+__global__ void scatter_full_kernel(int64_t nloc, const double* __restrict__ local, const int64_t* __restrict__ loc2glob, double* full) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (int64_t)gridDim.x * blockDim.x) full[loc2glob[i]] = local[i];
+}
+
 static int ew_grid(int64_t n, int device) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -207,10 +254,21 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
         int64_t vl = 0;
         for (int64_t k = 0; k < mat_num; ++k) { CUADMM_REQUIRE(blk[k] >= 1, "block size must be >= 1"); vl += (int64_t)blk[k] * (blk[k] + 1) / 2; }
         CUADMM_REQUIRE(vl == vec_len, "vec_len does not match the block sizes");
+        BlockLayout full_layout;
+        full_layout.init(blk, mat_num);
+        shard.build(full_layout, world, rank);      // world == 1: everything is local
+        nloc = shard.vec_len_local;
         plan.reset(new cuadmm_plan());
-        plan->layout.init(blk, mat_num);
+        plan->layout.init(shard.local_blk.data(), (int64_t)shard.local_blk.size());
         plan->device = device;
         plan->build_device();
+        if (world > 1) {
+            comm.reset(new NcclComm());
+            comm->init(rank, world, nccl_id, device);
+            red_buf.alloc(con_num + 2);
+            d_loc2glob.upload(shard.loc2glob);
+            use_graphs = false;                      // NCCL calls are enqueued directly
+        }
     }
     // ---- A: normalise the constraints (get_normA, src/solver.cu:79-80), same arithmetic
     std::vector<double> vals(At_vals, At_vals + At_nnz);
@@ -224,12 +282,23 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
         for (int p = At_col_ptrs[i]; p < At_col_ptrs[i + 1]; ++p) vals[p] /= norm;
     }
     // A in CSR is the CSC of At as given; At in CSR by a counting-sort transpose (csr2csc in the reference)
-    A = spmv_create(con_num, vec_len, At_nnz, At_col_ptrs, At_row_ids, vals.data(), device);
-    std::vector<int32_t> t_rp(vec_len + 1), t_ci(std::max<int64_t>(At_nnz, 1));
-    std::vector<double> t_v(std::max<int64_t>(At_nnz, 1));
-    if (cuadmm_csc_to_csr_host(vec_len, con_num, At_nnz, At_col_ptrs, At_row_ids, vals.data(), t_rp.data(), t_ci.data(), t_v.data()) != 0)
-        throw Error(CUADMM_EINVAL, cuadmm_last_error());
-    At = spmv_create(vec_len, con_num, At_nnz, t_rp.data(), t_ci.data(), t_v.data(), device);
+    {
+        // this rank's column slice A[:, I_g] (all of A on one GPU)
+        std::vector<int32_t> l_cp, l_ri; std::vector<double> l_v;
+        const int32_t* cp = At_col_ptrs; const int32_t* ri = At_row_ids; const double* vv = vals.data();
+        int64_t l_nnz = At_nnz;
+        if (world > 1) {
+            shard.slice_csc(con_num, At_col_ptrs, At_row_ids, vals.data(), l_cp, l_ri, l_v);
+            l_ri.push_back(0); l_v.push_back(0.0);   // keep data() valid when the slice is empty
+            cp = l_cp.data(); ri = l_ri.data(); vv = l_v.data(); l_nnz = l_cp[con_num];
+        }
+        A = spmv_create(con_num, nloc, l_nnz, cp, ri, vv, device);
+        std::vector<int32_t> t_rp(nloc + 1), t_ci(std::max<int64_t>(l_nnz, 1));
+        std::vector<double> t_v(std::max<int64_t>(l_nnz, 1));
+        if (cuadmm_csc_to_csr_host(nloc, con_num, l_nnz, cp, ri, vv, t_rp.data(), t_ci.data(), t_v.data()) != 0)
+            throw Error(CUADMM_EINVAL, cuadmm_last_error());
+        At = spmv_create(nloc, con_num, l_nnz, t_rp.data(), t_ci.data(), t_v.data(), device);
+    }
     // ---- A A^T factorisation (src/solver.cu:91-110), eps = 1e-15
     ys = ysolve_create(con_num, vec_len, At_nnz, At_col_ptrs, At_row_ids, vals.data(), 1e-15, device);
 
@@ -273,12 +342,19 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
 
     // ---- device vectors
     auto up = [&](DevBuf<double>& d, const std::vector<double>& h) { d.alloc(std::max<int64_t>((int64_t)h.size(), 1)); d.upload(h.data(), (int64_t)h.size(), stream); };
+    if (world > 1) {   // keep only the owned svec ranges of X, S, S-C, C
+        std::vector<double> t;
+        shard.slice_vec(hX.data(), t); hX.swap(t);
+        shard.slice_vec(hS.data(), t); hS.swap(t);
+        shard.slice_vec(hSmC.data(), t); hSmC.swap(t);
+        shard.slice_vec(hC.data(), t); hC.swap(t);
+    }
     up(X, hX); up(S, hS); up(y, hy); up(Rp, hRp); up(SmC, hSmC); up(Cd, hC); up(bd, hb); up(normA, h_normA);
-    Rd1.alloc(std::max<int64_t>(vec_len, 1)); Rd.alloc(std::max<int64_t>(vec_len, 1)); Xb.alloc(std::max<int64_t>(vec_len, 1));
-    Xproj.alloc(std::max<int64_t>(vec_len, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1));
+    Rd1.alloc(std::max<int64_t>(nloc, 1)); Rd.alloc(std::max<int64_t>(nloc, 1)); Xb.alloc(std::max<int64_t>(nloc, 1));
+    Xproj.alloc(std::max<int64_t>(nloc, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1));
     Rd1.zero(stream); Rd.zero(stream);
-    nA_blocks = spmv_grid(*A); nAt_blocks = spmv_grid(*At); nE_blocks = ew_grid(vec_len, device);
-    partial.alloc(2 * (int64_t)(std::max(nAt_blocks, nE_blocks) + nA_blocks) + 4);
+    nA_blocks = spmv_grid(*A); nAt_blocks = spmv_grid(*At); nE_blocks = ew_grid(std::max(nloc, con_num), device);
+    partial.alloc(2 * (int64_t)(std::max(nAt_blocks, nE_blocks) + std::max(nA_blocks, nE_blocks)) + 4);
     partial.zero(stream);
 
     st.alloc(1);
@@ -318,9 +394,21 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         prof_ev.push_back(ev);
         (void)k;
     };
-    // K1
-    e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
-    spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+    const int gm_ = ew_grid(con_num, device);
+    // K1  (multi-GPU: partial -A_g (S-C)_g, all-reduce, then rhsy = Rp/sig + sum)
+    auto k1 = [&]() {
+        if (world == 1) {
+            e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
+            spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+        } else {
+            e = SpmvEpilogue();
+            spmv_launch(*A, -1.0, SmC.p, 0.0, red_buf.p, e, stream);
+            comm->allreduce_sum(red_buf.p, con_num, stream);
+            rhsy_kernel<<<gm_, 256, 0, stream>>>(con_num, Rp.p, red_buf.p, rhsy.p, st.p);
+            launches += 3;
+        }
+    };
+    k1();
     // K2
     mark(0);
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
@@ -336,17 +424,16 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
     mark(3);
     if (iter == switch_admm) {
         switch_kernel<<<1, 1, 0, stream>>>(st.p); ++launches;
-        CUADMM_CUDA(cudaMemcpyAsync(X_best.p, X.p, sizeof(double) * vec_len, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(X_best.p, X.p, sizeof(double) * nloc, cudaMemcpyDeviceToDevice, stream));
         CUADMM_CUDA(cudaMemcpyAsync(y_best.p, y.p, sizeof(double) * con_num, cudaMemcpyDeviceToDevice, stream));
-        CUADMM_CUDA(cudaMemcpyAsync(S_best.p, S.p, sizeof(double) * vec_len, cudaMemcpyDeviceToDevice, stream));
+        CUADMM_CUDA(cudaMemcpyAsync(S_best.p, S.p, sizeof(double) * nloc, cudaMemcpyDeviceToDevice, stream));
     }
     double* part_rd = partial.p;
     double* part_rp = partial.p + 2 * (int64_t)std::max(nAt_blocks, nE_blocks);
     int n_rd = 0;
     if (iter < switch_admm) {
         // K5-K7: the sGS second half-step
-        e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
-        spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+        k1();
         mark(4);
         ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
         mark(5);
@@ -355,22 +442,32 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         n_rd = nAt_blocks;
     } else {
         if (iter > switch_admm) {
-            const int g = ew_grid(vec_len, device);
+            const int g = ew_grid(nloc, device);
             best_decide_kernel<<<1, 1, 0, stream>>>(st.p);
-            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, vec_len, X.p, X_best.p);
+            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, nloc, X.p, X_best.p);
             best_copy_kernel<<<g, 256, 0, stream>>>(st.p, con_num, y.p, y_best.p);
-            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, vec_len, S.p, S_best.p);
+            best_copy_kernel<<<g, 256, 0, stream>>>(st.p, nloc, S.p, S_best.p);
             launches += 4;
         }
         mark(4); mark(5);
-        x_update_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(vec_len, Rd1.p, S.p, Cd.p, Rd.p, X.p, st.p, part_rd); ++launches;
+        x_update_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(nloc, Rd1.p, S.p, Cd.p, Rd.p, X.p, st.p, part_rd); ++launches;
         n_rd = nE_blocks;
     }
-    // K8
-    e = SpmvEpilogue(); e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = part_rp;
-    spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream); ++launches;
-    // K9
-    scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, part_rd, n_rd, part_rp, nA_blocks, hist.p, hist_cap); ++launches;
+    // K8  (multi-GPU: partial A_g X_g plus the two local sums of K7 ride one all-reduce)
+    if (world == 1) {
+        e = SpmvEpilogue(); e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = part_rp;
+        spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream); ++launches;
+        // K9
+        scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, part_rd, n_rd, part_rp, nA_blocks, hist.p, hist_cap); ++launches;
+    } else {
+        e = SpmvEpilogue();
+        spmv_launch(*A, 1.0, X.p, 0.0, red_buf.p, e, stream);
+        fold_partials_kernel<<<1, 256, 0, stream>>>(part_rd, n_rd, red_buf.p + con_num, st.p);
+        comm->allreduce_sum(red_buf.p, con_num + 2, stream);
+        rp_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(con_num, bd.p, red_buf.p, normA.p, y.p, Rp.p, st.p, part_rp);
+        scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, red_buf.p + con_num, 1, part_rp, nE_blocks, hist.p, hist_cap);
+        launches += 5;
+    }
     CUADMM_CUDA(cudaGetLastError());
 }
 
@@ -408,8 +505,15 @@ void cuadmm_solver::launch_iteration(int iter, int switch_admm, bool prof) {
 void cuadmm_solver::enqueue_half_step() {
     const double* scal = &st.p->sig;
     SpmvEpilogue e;
-    e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
-    spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+    if (world == 1) {
+        e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
+        spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
+    } else {
+        spmv_launch(*A, -1.0, SmC.p, 0.0, red_buf.p, e, stream);
+        comm->allreduce_sum(red_buf.p, con_num, stream);
+        rhsy_kernel<<<ew_grid(con_num, device), 256, 0, stream>>>(con_num, Rp.p, red_buf.p, rhsy.p, st.p);
+        launches += 3;
+    }
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
 }
 
@@ -458,6 +562,18 @@ void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double 
     CUADMM_CUDA(cudaStreamSynchronize(stream));
 }
 
+// full-length X / S on every rank: scatter the owned ranges into a zeroed vector, sum all-reduce
+void cuadmm_solver::gather_full(const DevBuf<double>& local, double* h_full) {
+    CUADMM_REQUIRE(initialised && h_full, "solver not initialised");
+    CUADMM_CUDA(cudaSetDevice(device));
+    if (full_buf.n < vec_len) full_buf.alloc(std::max<int64_t>(vec_len, 1));
+    full_buf.zero(stream);
+    scatter_full_kernel<<<ew_grid(nloc, device), 256, 0, stream>>>(nloc, local.p, d_loc2glob.p, full_buf.p);
+    comm->allreduce_sum(full_buf.p, vec_len, stream);
+    full_buf.download(h_full, vec_len, stream);
+    CUADMM_CUDA(cudaStreamSynchronize(stream));
+}
+
 static bool is_log_iter(int iter) { return (iter <= 200 && iter % 50 == 1) || (iter > 200 && iter % 100 == 1); }
 
 void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshold, int sig_update_stage_1,
@@ -467,7 +583,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     CUADMM_REQUIRE(sig_update_stage_1 >= 1 && sig_update_stage_2 >= 1, "sig_update_stage must be >= 1");
     CUADMM_CUDA(cudaSetDevice(device));
     const auto t0 = std::chrono::steady_clock::now();
-    const int64_t n = vec_len, m = con_num;
+    const int64_t n = nloc, m = con_num;
     const int gv = ew_grid(n, device), gm = ew_grid(m, device);
     if (X_best.n < std::max<int64_t>(n, 1)) {   // always allocated: the ADMM graph bakes these pointers
         X_best.alloc(std::max<int64_t>(n, 1)); y_best.alloc(std::max<int64_t>(m, 1)); S_best.alloc(std::max<int64_t>(n, 1));
@@ -492,8 +608,15 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
         sub_kernel<<<gv, 256, 0, stream>>>(n, S.p, Cd.p, SmC.p);
         h_st->done = 0;
         CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
-        SpmvEpilogue e; e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = partial.p;
-        spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream);
+        if (world == 1) {
+            SpmvEpilogue e; e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = partial.p;
+            spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream);
+        } else {
+            SpmvEpilogue e;
+            spmv_launch(*A, 1.0, X.p, 0.0, red_buf.p, e, stream);
+            comm->allreduce_sum(red_buf.p, con_num, stream);
+            rp_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(con_num, bd.p, red_buf.p, normA.p, y.p, Rp.p, st.p, partial.p);
+        }
         launches += 5;
     }
     h_st->iter = 1;
@@ -512,6 +635,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
     CUADMM_CUDA(cudaStreamSynchronize(stream));
 
+    if (rank != 0) verbose = false;   // one log per job
     if (verbose) {
         printf("\n -------------------------------------------------------------------------------");
         printf("\n                                    cuADMM");
@@ -636,17 +760,37 @@ static void get_vec(cuadmm_solver_t* s, const DevBuf<double>& d, int64_t n, doub
     d.download(h, n, s->stream);
     CUADMM_CUDA(cudaStreamSynchronize(s->stream));
 }
-int cuadmm_solver_get_X(cuadmm_solver_t* s, double* h) { return guarded([&] { get_vec(s, s->X, s->vec_len, h); }); }
+int cuadmm_solver_get_X(cuadmm_solver_t* s, double* h) {
+    return guarded([&] { if (s && s->world > 1) s->gather_full(s->X, h); else get_vec(s, s->X, s->vec_len, h); });
+}
 int cuadmm_solver_get_y(cuadmm_solver_t* s, double* h) { return guarded([&] { get_vec(s, s->y, s->con_num, h); }); }
-int cuadmm_solver_get_S(cuadmm_solver_t* s, double* h) { return guarded([&] { get_vec(s, s->S, s->vec_len, h); }); }
+int cuadmm_solver_get_S(cuadmm_solver_t* s, double* h) {
+    return guarded([&] { if (s && s->world > 1) s->gather_full(s->S, h); else get_vec(s, s->S, s->vec_len, h); });
+}
+
+int cuadmm_solver_set_distributed(cuadmm_solver_t* s, int rank, int world, const char id[128]) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && id, "null argument");
+        CUADMM_REQUIRE(!s->initialised, "set_distributed must precede init");
+        CUADMM_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+        s->rank = rank; s->world = world;
+        memcpy(s->nccl_id, id, 128);
+    });
+}
 
 int cuadmm_solver_set_XyS(cuadmm_solver_t* s, const double* h_X, const double* h_y, const double* h_S, double sig) {
     return guarded([&] {
         CUADMM_REQUIRE(s && s->initialised, "solver not initialised");
         CUADMM_CUDA(cudaSetDevice(s->device));
-        if (h_X) s->X.upload(h_X, s->vec_len, s->stream);
+        std::vector<double> lx, ls;
+        if (s->world > 1) {
+            if (h_X) { s->shard.slice_vec(h_X, lx); h_X = lx.data(); }
+            if (h_S) { s->shard.slice_vec(h_S, ls); h_S = ls.data(); }
+        }
+        if (h_X) s->X.upload(h_X, s->nloc, s->stream);
         if (h_y) s->y.upload(h_y, s->con_num, s->stream);
-        if (h_S) s->S.upload(h_S, s->vec_len, s->stream);
+        if (h_S) s->S.upload(h_S, s->nloc, s->stream);
+        CUADMM_CUDA(cudaStreamSynchronize(s->stream));
         CUADMM_CUDA(cudaMemcpyAsync(&s->st.p->sig, &sig, sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUADMM_CUDA(cudaStreamSynchronize(s->stream));
     });

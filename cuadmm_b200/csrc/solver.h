@@ -8,6 +8,8 @@
 #include "spmv.h"
 #include "ysolve.h"
 #include "problem.h"
+#include "shard.h"
+#include "dist.h"
 
 namespace cuadmm {
 
@@ -33,6 +35,16 @@ struct cuadmm_solver {
     bool verbose = false;
     bool initialised = false;
     int64_t vec_len = 0, con_num = 0;
+    int64_t nloc = 0;                        // svec entries owned by this rank (== vec_len on one GPU)
+    // multi-GPU (one process per GPU): block shard + NCCL communicator
+    int rank = 0, world = 1;
+    char nccl_id[128] = {0};
+    cuadmm::Shard shard;
+    std::unique_ptr<cuadmm::NcclComm> comm;
+    cuadmm::DevBuf<double> red_buf;          // m + 2 doubles: partial A_g x_g + two scalars, all-reduced in place
+    cuadmm::DevBuf<int64_t> d_loc2glob;
+    cuadmm::DevBuf<double> full_buf;         // vec_len doubles, for gathering full X / S
+    void gather_full(const cuadmm::DevBuf<double>& local, double* h_full);
     std::unique_ptr<cuadmm_plan> plan;
     cuadmm_spmv_s* A = nullptr;    // m x vec_len (row-normalised)
     cuadmm_spmv_s* At = nullptr;   // vec_len x m

@@ -184,6 +184,28 @@ int  cuadmm_solver_run_iterations(cuadmm_solver_t* s, int n_iters, int sgs, int 
 /* y-solve statistics of the solver's factorisation (see cuadmm_ysolve_stats) */
 int  cuadmm_solver_ysolve_stats(const cuadmm_solver_t* s, int64_t out[8]);
 
+/* --------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU.  Blocks are sharded by eig cost (cuadmm_plan_partition); every rank
+ * owns X, S, C on its svec ranges and the column slice A[:, I_g]; the only per-iteration traffic is an
+ * NCCL sum all-reduce of the m-vector partial products A[:, I_g] x_g (3 per sGS iteration, 2 per ADMM
+ * iteration).  Replaces SDPDuoSolver's GPU workers + cudaMemcpyPeerAsync of dense blocks
+ * (src/duo_solver.cu:266-336, 487-577).  Call cuadmm_solver_set_distributed BEFORE cuadmm_solver_init,
+ * with the same 128-byte id on every rank (rank 0 creates it with cuadmm_nccl_unique_id and the launcher
+ * broadcasts it); init/solve then take the FULL problem on every rank, get_X/get_S return full vectors.
+ * -------------------------------------------------------------------------- */
+int  cuadmm_nccl_unique_id(char out[128]);
+int  cuadmm_solver_set_distributed(cuadmm_solver_t* s, int rank, int world, const char id[128]);
+/* sharding logic on its own (host only; CPU tests): */
+typedef struct cuadmm_shard cuadmm_shard_t;
+int  cuadmm_shard_create(const int32_t* blk, int64_t nblk, int world, int rank, cuadmm_shard_t** out);
+void cuadmm_shard_destroy(cuadmm_shard_t* s);
+/* out[0..3] = local svec length, local block count, global svec length, world */
+int  cuadmm_shard_info(const cuadmm_shard_t* s, int64_t out[4]);
+int  cuadmm_shard_maps(const cuadmm_shard_t* s, int32_t* local_blk, int64_t* local_block_ids, int64_t* loc2glob, int32_t* owner);
+/* At (vec_len x ncols, CSC) -> rows owned by this rank, renumbered locally; returns the local nnz */
+int64_t cuadmm_shard_slice_csc(const cuadmm_shard_t* s, int64_t ncols, const int32_t* col_ptrs, const int32_t* row_ids,
+                               const double* vals, int32_t* out_col_ptrs, int32_t* out_row_ids, double* out_vals);
+
 /* MEX-shaped one-shot entry: the cuadmm_MATLAB signature
  * (MATLAB/cuadmm_MATLAB.cu:197-433) over plain arrays.  At_stack is CSC
  * (vec_len x m), b / C_stack sparse columns, blk_vec doubles, X0/y0/S0 dense.
