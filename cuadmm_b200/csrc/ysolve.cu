@@ -28,85 +28,123 @@ static constexpr int kNarrowThreads = 1024;
 //                   handshake; the deep end of the elimination DAG is hundreds of levels a few rows wide).
 // No spin-waiting anywhere, so no co-residency requirement and nothing to deadlock.
 // Unknown u:  x[u] = (rhs[u] - sum_p val[p] * x[dep[p]]) * inv_diag[u].
-__device__ __forceinline__ void tri_slot(int64_t s, int lane, const int32_t* __restrict__ slot_rows, int is_long,
-        const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep, const double* __restrict__ val,
-        const double* __restrict__ inv_diag, const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
-        double* x, double* out_scatter, const int32_t* __restrict__ out_perm) {
-    double acc = 0.0;
-    int32_t u;
-    if (is_long) {
-        u = slot_rows[8 * s];
-        const int64_t p1 = ptr[u + 1];
-#pragma unroll 4
-        for (int64_t p = ptr[u] + lane; p < p1; p += 32) acc = fma(val[p], x[dep[p]], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    } else {
-        u = slot_rows[8 * s + (lane >> 2)];
+// Everything of a slot that does not depend on x (structure, values, right-hand side) is loaded by
+// SlotWork::load and can therefore be issued one level AHEAD of the level barrier; finish() then
+// only has the x loads on its critical path.  The deep end of the elimination DAG is latency-bound:
+// this turns a chain of five dependent global loads per level into one.
+struct SlotWork {
+    static constexpr int K = 4;        // entries per lane kept in registers
+    int32_t u; int is_long;
+    double rv, invd;
+    int64_t p, p1; int step;
+    int32_t d[K]; double v[K];
+
+    __device__ __forceinline__ void load(int64_t s, int lane, const int32_t* __restrict__ slot_rows,
+            const int32_t* __restrict__ slot_info, const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep,
+            const double* __restrict__ val, const double* __restrict__ inv_diag, const double* __restrict__ rhs,
+            const int32_t* __restrict__ rhs_gather) {
+        is_long = slot_info[s] >> 30;
+        u = slot_rows[8 * s + (is_long ? 0 : (lane >> 2))];
+        step = is_long ? 32 : 4;
+        p = 0; p1 = 0; rv = 0.0; invd = 0.0;
         if (u >= 0) {
-            const int64_t p1 = ptr[u + 1];
-            for (int64_t p = ptr[u] + (lane & 3); p < p1; p += 4) acc = fma(val[p], x[dep[p]], acc);
+            p = ptr[u] + (is_long ? lane : (lane & 3));
+            p1 = ptr[u + 1];
+            invd = inv_diag[u];
+            rv = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
         }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int64_t q = p + (int64_t)k * step;
+            if (q < p1) { d[k] = dep[q]; v[k] = val[q]; } else { d[k] = -1; v[k] = 0.0; }
+        }
+    }
+    __device__ __forceinline__ void finish(int lane, const int32_t* __restrict__ dep, const double* __restrict__ val,
+                                           double* x, double* out_scatter, const int32_t* __restrict__ out_perm) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (d[k] >= 0) acc = fma(v[k], x[d[k]], acc);
+        for (int64_t q = p + (int64_t)K * step; q < p1; q += step) acc = fma(val[q], x[dep[q]], acc);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (is_long) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        }
+        const bool writer = (u >= 0) && (is_long ? (lane == 0) : ((lane & 3) == 0));
+        if (writer) {
+            const double r = (rv - acc) * invd;
+            x[u] = r;
+            if (out_scatter) out_scatter[out_perm[u]] = r;
+        }
     }
-    const bool writer = is_long ? (lane == 0) : ((lane & 3) == 0 && u >= 0);
-    if (writer) {
-        const double r = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
-        const double v = (r - acc) * inv_diag[u];
-        x[u] = v;
-        if (out_scatter) out_scatter[out_perm[u]] = v;
-    }
-}
+};
 
-__global__ void __launch_bounds__(kTriThreads) tri_wide_kernel(
-        int64_t slot0, int64_t slot1, const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info,
-        const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep, const double* __restrict__ val,
-        const double* __restrict__ inv_diag, const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
-        double* x, double* out_scatter, const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
+#define CUADMM_TRI_PARAMS                                                                                   \
+    const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info, const int64_t* __restrict__ ptr, \
+    const int32_t* __restrict__ dep, const double* __restrict__ val, const double* __restrict__ inv_diag,   \
+    const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter, \
+    const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag
+#define CUADMM_TRI_LOAD(W, S) (W).load((S), lane, slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather)
+#define CUADMM_TRI_FINISH(W) (W).finish(lane, dep, val, x, out_scatter, out_perm)
+
+__global__ void __launch_bounds__(kTriThreads) tri_wide_kernel(int64_t slot0, int64_t slot1, CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
     const int lane = threadIdx.x & 31;
     const int64_t s = slot0 + (((int64_t)blockIdx.x * kTriThreads + threadIdx.x) >> 5);
     if (s >= slot1) return;
-    tri_slot(s, lane, slot_rows, slot_info[s] >> 30, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm);
+    SlotWork w;
+    CUADMM_TRI_LOAD(w, s);
+    CUADMM_TRI_FINISH(w);
 }
 
-__global__ void __launch_bounds__(kNarrowThreads) tri_narrow_kernel(
-        int level0, int level1, const int64_t* __restrict__ level_ptr, const int32_t* __restrict__ slot_rows,
-        const int32_t* __restrict__ slot_info, const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep,
-        const double* __restrict__ val, const double* __restrict__ inv_diag, const double* __restrict__ rhs,
-        const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter, const int32_t* __restrict__ out_perm,
-        const int* __restrict__ done_flag) {
-    if (done_flag && *done_flag) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// levels [level0, level1) of lvl_ptr inside one CTA of NW warps; the first slot of the next level is
+// prefetched (static part) before the barrier of the current one
+template <int NW>
+__device__ __forceinline__ void tri_level_loop(const int64_t* __restrict__ lvl_ptr, int level0, int level1, int lane, int warp,
+        CUADMM_TRI_PARAMS) {
+    (void)done_flag;
+    if (level0 >= level1) return;
+    SlotWork w;
+    int64_t s0 = lvl_ptr[level0];
+    int64_t s1 = lvl_ptr[level0 + 1];
+    bool have = (s0 + warp) < s1;
+    if (have) CUADMM_TRI_LOAD(w, s0 + warp);
     for (int l = level0; l < level1; ++l) {
-        const int64_t s1 = level_ptr[l + 1];
-        for (int64_t s = level_ptr[l] + warp; s < s1; s += kNarrowThreads / 32)
-            tri_slot(s, lane, slot_rows, slot_info[s] >> 30, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm);
+        if (have) {
+            CUADMM_TRI_FINISH(w);
+            for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
+        }
+        s0 = s1;
+        have = false;
+        if (l + 1 < level1) {
+            s1 = lvl_ptr[l + 2];
+            have = (s0 + warp) < s1;
+            if (have) CUADMM_TRI_LOAD(w, s0 + warp);
+        }
         __syncthreads();   // also makes this CTA's global writes visible to its own later loads
     }
+}
+
+__global__ void __launch_bounds__(kNarrowThreads) tri_narrow_kernel(int level0, int level1, const int64_t* __restrict__ level_ptr,
+                                                                    CUADMM_TRI_PARAMS) {
+    if (done_flag && *done_flag) return;
+    tri_level_loop<kNarrowThreads / 32>(level_ptr, level0, level1, threadIdx.x & 31, threadIdx.x >> 5,
+        slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag);
 }
 
 // Subtree parallelism: every CTA owns one subtree of the elimination tree (all of whose dependencies
 // are inside the subtree, or already final), and walks the subtree's own levels with __syncthreads.
 // Thousands of independent deep chains (one per block neighbourhood of a moment relaxation) thus cost
-// ONE launch and depth x ~0.3 us instead of depth x (kernel boundary).
-__global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(
-        const int64_t* __restrict__ sub_off, const int64_t* __restrict__ sub_lvl_ptr,
-        const int32_t* __restrict__ slot_rows, const int32_t* __restrict__ slot_info,
-        const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep, const double* __restrict__ val,
-        const double* __restrict__ inv_diag, const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather,
-        double* x, double* out_scatter, const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
+// ONE launch and depth x (one x-load latency) instead of depth x (kernel boundary).
+__global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t* __restrict__ sub_off,
+        const int64_t* __restrict__ sub_lvl_ptr, CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t base = sub_off[blockIdx.x];
     const int nl = (int)(sub_off[blockIdx.x + 1] - base) - 1;
-    for (int l = 0; l < nl; ++l) {
-        const int64_t s1 = sub_lvl_ptr[base + l + 1];
-        for (int64_t s = sub_lvl_ptr[base + l] + warp; s < s1; s += kTriThreads / 32)
-            tri_slot(s, lane, slot_rows, slot_info[s] >> 30, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm);
-        __syncthreads();
-    }
+    tri_level_loop<kTriThreads / 32>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, threadIdx.x >> 5,
+        slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag);
 }
 
 // dense tail: out[i] = sum_j T[i, j] * in[j] for a row-major r x r matrix of which only the
@@ -282,6 +320,8 @@ static int64_t choose_subtrees(const CholFactor& F, int64_t n_lead, std::vector<
     int64_t cap = 32768;
     if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_CAP")) cap = atoll(e);
     if (cap <= 0) return 0;
+    int64_t min_size = 2;         // (measured: peeling small subtrees off into extra top levels costs more than their CTAs)
+    if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_MIN")) min_size = atoll(e);
     std::vector<int64_t> size(n, 1);
     for (int64_t v = 0; v < n_lead; ++v) {
         const int32_t p = F.parent[v];
@@ -293,7 +333,7 @@ static int64_t choose_subtrees(const CholFactor& F, int64_t n_lead, std::vector<
         const bool parent_top = (p < 0 || p >= n_lead || sub[p] < 0);
         if (!parent_top) { sub[v] = sub[p]; continue; }
         const bool parent_fits = (p >= 0 && p < n_lead && size[p] <= cap);
-        if (size[v] <= cap && !parent_fits && size[v] >= 2) sub[v] = (int32_t)n_sub++;
+        if (size[v] <= cap && !parent_fits && size[v] >= min_size) sub[v] = (int32_t)n_sub++;
     }
     return n_sub;
 }
