@@ -4,6 +4,13 @@
 #include "blocks.h"
 #include "project_jacobi.cuh"
 
+namespace cuadmm { struct DensePart; }
+cuadmm::DensePart* dense_part_create(int device, const std::vector<int32_t>& blk, const std::vector<int64_t>& svec_off,
+                                     const std::vector<int64_t>& which);
+void dense_part_destroy(cuadmm::DensePart* p);
+int dense_part_project(cuadmm::DensePart* D, const double* Xb, double* Xproj, cudaStream_t st,
+                       const cuadmm::ProjEpilogue* epi, const int* done_flag);
+
 struct cuadmm_plan {
     int device = -1;
     cuadmm::BlockLayout layout;
@@ -35,6 +42,7 @@ struct cuadmm_plan {
     std::vector<cudaStream_t> side_streams;    // classes run concurrently on these
     std::vector<cudaEvent_t> side_events;
     cudaEvent_t fork_event = nullptr;
+    cuadmm::DensePart* dense = nullptr;        // blocks n > 168: GEMM-only sign-function path (dense_proj.cu)
     const int* done_flag = nullptr;            // device stop flag honoured by the kernels (solver)
     double last_ms = 0.0;
     int64_t last_launches = 0;

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <numeric>
 #include <stdlib.h>
+#include <string.h>
 
 namespace cuadmm {
 
@@ -551,6 +552,7 @@ cuadmm_plan::~cuadmm_plan() {
         if (fork_event) cudaEventDestroy(fork_event);
         for (auto s : side_streams) cudaStreamDestroy(s);
         for (auto e : side_events) cudaEventDestroy(e);
+        if (dense) dense_part_destroy(dense);
     }
 }
 
@@ -563,12 +565,18 @@ void cuadmm_plan::build_device() {
     // classify
     const std::vector<SizeClass> table = size_classes();
     std::vector<std::vector<int64_t>> members(table.size() + 1);
+    const char* large_env = getenv("CUADMM_LARGE");           // "jacobi": global-memory Jacobi for n > 168 (debug)
+    const bool large_dense = !(large_env && !strcmp(large_env, "jacobi"));
+    std::vector<int64_t> dense_blocks;
     for (int64_t k = 0; k < nblk; ++k) {
         const int n = layout.blk[k];
         size_t ci = table.size();
         for (size_t c = 0; c < table.size(); ++c) if (n <= table[c].nmax) { ci = c; break; }
+        if (ci == table.size() && large_dense) { dense_blocks.push_back(k); continue; }
         members[ci].push_back(k);
     }
+    if (dense) { dense_part_destroy(dense); dense = nullptr; }
+    if (!dense_blocks.empty()) dense = dense_part_create(device, layout.blk, layout.svec_off, dense_blocks);
     h_desc.clear(); classes.clear();
     int64_t scratch = 0;
     // heaviest classes first so their launches start first
@@ -619,7 +627,7 @@ void cuadmm_plan::build_device() {
     CUADMM_CUDA(cudaEventCreate(&ev0));
     CUADMM_CUDA(cudaEventCreate(&ev1));
     CUADMM_CUDA(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
-    for (size_t i = 1; i < classes.size(); ++i) {
+    for (size_t i = 0; i < classes.size(); ++i) {
         cudaStream_t s; cudaEvent_t e;
         CUADMM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         CUADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -637,13 +645,19 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
                          const ProjEpilogue* epi, bool want_eig) {
     if (device < 0) throw Error(CUADMM_ENODEVICE, "plan was built without a CUDA device; there is no CPU fallback");
     int launches = 0;
-    // fork: class i>0 runs on its own stream so small and mid classes overlap
-    if (classes.size() > 1) CUADMM_CUDA(cudaEventRecord(fork_event, stream));
+    // blocks on the dense path produce no eigenvalues: their debug slots read NaN
+    if (want_eig) CUADMM_CUDA(cudaMemsetAsync(d_eig.p, 0xFF, sizeof(double) * (size_t)d_eig.n, stream));
+    // fork: the dense (GEMM) part, if any, runs on the caller's stream; Jacobi classes run on side
+    // streams so that small, mid and large blocks overlap (class 0 stays on the caller's stream when
+    // there is no dense part)
+    const bool has_dense = dense != nullptr;
+    if (classes.size() > 1 || (has_dense && !classes.empty())) CUADMM_CUDA(cudaEventRecord(fork_event, stream));
     for (size_t i = 0; i < classes.size(); ++i) {
         const Class& cl = classes[i];
         cudaStream_t st = stream;
-        if (i > 0) {
-            st = side_streams[i - 1];
+        const bool side = has_dense || i > 0;
+        if (side) {
+            st = side_streams[i];
             CUADMM_CUDA(cudaStreamWaitEvent(st, fork_event, 0));
         }
         ProjArgs a;
@@ -664,11 +678,11 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
         }
         CUADMM_CUDA(cudaGetLastError());
         ++launches;
-        if (i > 0) {
-            CUADMM_CUDA(cudaEventRecord(side_events[i - 1], st));
-            CUADMM_CUDA(cudaStreamWaitEvent(stream, side_events[i - 1], 0));
-        }
+        if (side) CUADMM_CUDA(cudaEventRecord(side_events[i], st));
     }
+    if (has_dense) launches += dense_part_project(dense, d_Xb, d_Xproj, stream, epi, done_flag);
+    for (size_t i = 0; i < classes.size(); ++i)
+        if (has_dense || i > 0) CUADMM_CUDA(cudaStreamWaitEvent(stream, side_events[i], 0));
     return launches;
 }
 
