@@ -134,6 +134,23 @@ def run_reference(args):
                                        "(CHOLMOD-substitute); init %.1f s not counted" % (steps, threads, t_init)},
             "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host_cores": cores}
+    # Baseline A (informational): the reference's own cuSOLVER projection stage (src/solver.cu:531-647,
+    # unmodified reference sources in oracle/_ref) on GPU 0 of this box, same blocks, same input
+    try:
+        import ctypes as C
+        ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libcuadmm_ref.so"))
+        ref.ref_proj_create.restype = C.c_void_p
+        ref.ref_proj_run.restype = C.c_double
+        from cuadmm_b200.synthetic import random_svec
+        blk = np.ascontiguousarray(P["blk"], np.int32)
+        x = random_svec(blk, seed=0)
+        h = ref.ref_proj_create(blk.ctypes.data_as(C.POINTER(C.c_int)), len(blk), 15)
+        ms = ref.ref_proj_run(C.c_void_p(h), x.ctypes.data_as(C.POINTER(C.c_double)), None, 2)
+        ref.ref_proj_destroy(C.c_void_p(h))
+        line["baseline_A_cusolver_projection_ms"] = ms
+    except Exception as ex:
+        line["baseline_A_cusolver_projection_ms"] = None
+        line["baseline_A_note"] = "oracle/_ref not usable here: %s" % ex
     print(json.dumps(line), flush=True)
 
 
@@ -220,11 +237,16 @@ def run_ours(args):
         t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+    ys = s.ysolve_stats()
+    if dist is not None:
+        # leave the job together: the solver's NCCL communicator first, then torch's process group
+        s.close()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
     hbm, hbm_src = measured_peaks()
-    ys = s.ysolve_stats()
     value = args.steps / (ms_total / 1e3)
     alg_bytes = 56 * n                      # fused projection stage: reads Xb, X, Rd1, C; writes Xproj, S, SmC
     f_alg = float(sum((20.0 / 3.0) * float(b) ** 3 for b in P["blk"]))
@@ -260,8 +282,6 @@ def run_ours(args):
         except Exception as ex:   # the baseline is informational; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "iter/s", "cores": threads, "kind": "port", "sample": "failed: %s" % ex}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
