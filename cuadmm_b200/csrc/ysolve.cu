@@ -11,6 +11,7 @@
 #include "dense.h"
 #include <algorithm>
 #include <numeric>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace cuadmm {
@@ -19,6 +20,7 @@ static constexpr int kTriThreads = 256;
 static constexpr int kLongRowNnz = 24;     // rows with more dependencies get a whole warp
 static constexpr int kNarrowSlots = 160;   // levels with at most this many warp-slots run inside one CTA
 static constexpr int kNarrowThreads = 1024;
+static constexpr int kWarpSubRows = 32;     // subtrees up to this many unknowns are solved by one warp
 
 // Work of a triangular sweep is cut into warp-slots: a slot is either 8 short rows (4 lanes each) or
 // 1 long row (32 lanes), all of one dependency level.  The levels are grouped into phases:
@@ -34,37 +36,44 @@ static constexpr int kNarrowThreads = 1024;
 // this turns a chain of five dependent global loads per level into one.
 struct SlotWork {
     static constexpr int K = 4;        // entries per lane kept in registers
-    int32_t u; int is_long;
+    int32_t u, uloc; int is_long;
     double rv, invd;
     int64_t p, p1; int step;
-    int32_t d[K]; double v[K];
+    int32_t d[K], dl[K]; double v[K];
 
     __device__ __forceinline__ void load(int64_t s, int lane, const int32_t* __restrict__ slot_rows,
             const int32_t* __restrict__ slot_info, const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep,
             const double* __restrict__ val, const double* __restrict__ inv_diag, const double* __restrict__ rhs,
-            const int32_t* __restrict__ rhs_gather) {
+            const int32_t* __restrict__ rhs_gather, const int32_t* __restrict__ dep_loc, const int32_t* __restrict__ row_loc) {
         is_long = slot_info[s] >> 30;
         u = slot_rows[8 * s + (is_long ? 0 : (lane >> 2))];
         step = is_long ? 32 : 4;
-        p = 0; p1 = 0; rv = 0.0; invd = 0.0;
+        p = 0; p1 = 0; rv = 0.0; invd = 0.0; uloc = -1;
         if (u >= 0) {
             p = ptr[u] + (is_long ? lane : (lane & 3));
             p1 = ptr[u + 1];
             invd = inv_diag[u];
             rv = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
+            if (row_loc) uloc = row_loc[u];
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int64_t q = p + (int64_t)k * step;
-            if (q < p1) { d[k] = dep[q]; v[k] = val[q]; } else { d[k] = -1; v[k] = 0.0; }
+            if (q < p1) { d[k] = dep[q]; v[k] = val[q]; dl[k] = dep_loc ? dep_loc[q] : -1; }
+            else { d[k] = -1; v[k] = 0.0; dl[k] = -1; }
         }
     }
+    // xs: the subtree's unknowns in shared memory (null for the top-part kernels)
     __device__ __forceinline__ void finish(int lane, const int32_t* __restrict__ dep, const double* __restrict__ val,
-                                           double* x, double* out_scatter, const int32_t* __restrict__ out_perm) {
+                                           const int32_t* __restrict__ dep_loc, double* x, double* xs,
+                                           double* out_scatter, const int32_t* __restrict__ out_perm) {
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) if (d[k] >= 0) acc = fma(v[k], x[d[k]], acc);
-        for (int64_t q = p + (int64_t)K * step; q < p1; q += step) acc = fma(val[q], x[dep[q]], acc);
+        for (int k = 0; k < K; ++k) if (d[k] >= 0) acc = fma(v[k], (xs && dl[k] >= 0) ? xs[dl[k]] : x[d[k]], acc);
+        for (int64_t q = p + (int64_t)K * step; q < p1; q += step) {
+            const int32_t l = (xs && dep_loc) ? dep_loc[q] : -1;
+            acc = fma(val[q], l >= 0 ? xs[l] : x[dep[q]], acc);
+        }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         if (is_long) {
@@ -76,6 +85,7 @@ struct SlotWork {
         if (writer) {
             const double r = (rv - acc) * invd;
             x[u] = r;
+            if (xs && uloc >= 0) xs[uloc] = r;
             if (out_scatter) out_scatter[out_perm[u]] = r;
         }
     }
@@ -86,65 +96,238 @@ struct SlotWork {
     const int32_t* __restrict__ dep, const double* __restrict__ val, const double* __restrict__ inv_diag,   \
     const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter, \
     const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag
-#define CUADMM_TRI_LOAD(W, S) (W).load((S), lane, slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather)
-#define CUADMM_TRI_FINISH(W) (W).finish(lane, dep, val, x, out_scatter, out_perm)
+#define CUADMM_TRI_ARGS slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag
+#define CUADMM_TRI_LOAD(W, S) (W).load((S), lane, slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, dep_loc, row_loc)
+#define CUADMM_TRI_FINISH(W) (W).finish(lane, dep, val, dep_loc, x, xs, out_scatter, out_perm)
 
 __global__ void __launch_bounds__(kTriThreads) tri_wide_kernel(int64_t slot0, int64_t slot1, CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
     const int lane = threadIdx.x & 31;
     const int64_t s = slot0 + (((int64_t)blockIdx.x * kTriThreads + threadIdx.x) >> 5);
     if (s >= slot1) return;
+    const int32_t* dep_loc = nullptr; const int32_t* row_loc = nullptr; double* xs = nullptr;
     SlotWork w;
     CUADMM_TRI_LOAD(w, s);
     CUADMM_TRI_FINISH(w);
 }
 
-// levels [level0, level1) of lvl_ptr inside one CTA of NW warps; the first slot of the next level is
-// prefetched (static part) before the barrier of the current one
-template <int NW>
+// levels [level0, level1) of lvl_ptr inside one CTA of NW warps.  The x-independent part of a warp's
+// first slot is prefetched TWO levels ahead (two register sets), so that by the time a level starts
+// only the x values (shared memory for subtrees) are on the critical path.
+template <int NW, bool WARP>
 __device__ __forceinline__ void tri_level_loop(const int64_t* __restrict__ lvl_ptr, int level0, int level1, int lane, int warp,
-        CUADMM_TRI_PARAMS) {
+        const int32_t* __restrict__ dep_loc, const int32_t* __restrict__ row_loc, double* xs, CUADMM_TRI_PARAMS) {
     (void)done_flag;
     if (level0 >= level1) return;
-    SlotWork w;
-    int64_t s0 = lvl_ptr[level0];
-    int64_t s1 = lvl_ptr[level0 + 1];
-    bool have = (s0 + warp) < s1;
-    if (have) CUADMM_TRI_LOAD(w, s0 + warp);
-    for (int l = level0; l < level1; ++l) {
-        if (have) {
-            CUADMM_TRI_FINISH(w);
-            for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
+    SlotWork w0, w1;
+    bool h0 = false, h1 = false;
+    {
+        const int64_t a = lvl_ptr[level0] + warp;
+        h0 = a < lvl_ptr[level0 + 1];
+        if (h0) CUADMM_TRI_LOAD(w0, a);
+        if (level0 + 1 < level1) {
+            const int64_t b = lvl_ptr[level0 + 1] + warp;
+            h1 = b < lvl_ptr[level0 + 2];
+            if (h1) CUADMM_TRI_LOAD(w1, b);
         }
-        s0 = s1;
-        have = false;
-        if (l + 1 < level1) {
-            s1 = lvl_ptr[l + 2];
-            have = (s0 + warp) < s1;
-            if (have) CUADMM_TRI_LOAD(w, s0 + warp);
+    }
+    for (int l = level0; l < level1; l += 2) {
+        // ---- level l (register set 0)
+        {
+            const int64_t s0 = lvl_ptr[l], s1 = lvl_ptr[l + 1];
+            if (h0) {
+                CUADMM_TRI_FINISH(w0);
+                for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
+            }
+            h0 = false;
+            if (l + 2 < level1) {
+                const int64_t a = lvl_ptr[l + 2] + warp;
+                h0 = a < lvl_ptr[l + 3];
+                if (h0) CUADMM_TRI_LOAD(w0, a);
+            }
+            if constexpr (WARP) __syncwarp(); else __syncthreads();   // orders this level's writes before the next level's reads
         }
-        __syncthreads();   // also makes this CTA's global writes visible to its own later loads
+        if (l + 1 >= level1) break;
+        // ---- level l + 1 (register set 1)
+        {
+            const int64_t s0 = lvl_ptr[l + 1], s1 = lvl_ptr[l + 2];
+            if (h1) {
+                CUADMM_TRI_FINISH(w1);
+                for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
+            }
+            h1 = false;
+            if (l + 3 < level1) {
+                const int64_t b = lvl_ptr[l + 3] + warp;
+                h1 = b < lvl_ptr[l + 4];
+                if (h1) CUADMM_TRI_LOAD(w1, b);
+            }
+            if constexpr (WARP) __syncwarp(); else __syncthreads();
+        }
     }
 }
 
 __global__ void __launch_bounds__(kNarrowThreads) tri_narrow_kernel(int level0, int level1, const int64_t* __restrict__ level_ptr,
                                                                     CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
-    tri_level_loop<kNarrowThreads / 32>(level_ptr, level0, level1, threadIdx.x & 31, threadIdx.x >> 5,
-        slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag);
+    tri_level_loop<kNarrowThreads / 32, false>(level_ptr, level0, level1, threadIdx.x & 31, threadIdx.x >> 5,
+                                        nullptr, nullptr, nullptr, CUADMM_TRI_ARGS);
 }
 
 // Subtree parallelism: every CTA owns one subtree of the elimination tree (all of whose dependencies
-// are inside the subtree, or already final), and walks the subtree's own levels with __syncthreads.
-// Thousands of independent deep chains (one per block neighbourhood of a moment relaxation) thus cost
-// ONE launch and depth x (one x-load latency) instead of depth x (kernel boundary).
+// are inside the subtree, or already final), keeps the subtree's unknowns in SHARED MEMORY and walks
+// the subtree's own levels with __syncthreads.  Thousands of independent deep chains (one per block
+// neighbourhood of a moment relaxation) thus cost ONE launch and depth x (shared-memory round trip)
+// instead of depth x (kernel boundary) or depth x (L2 round trip).
 __global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t* __restrict__ sub_off,
-        const int64_t* __restrict__ sub_lvl_ptr, CUADMM_TRI_PARAMS) {
+        const int64_t* __restrict__ sub_lvl_ptr, const int32_t* __restrict__ dep_loc, const int32_t* __restrict__ row_loc,
+        CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
+    extern __shared__ double tri_xs[];
     const int64_t base = sub_off[blockIdx.x];
     const int nl = (int)(sub_off[blockIdx.x + 1] - base) - 1;
-    tri_level_loop<kTriThreads / 32>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, threadIdx.x >> 5,
-        slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag);
+    tri_level_loop<kTriThreads / 32, false>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, threadIdx.x >> 5,
+                                            dep_loc, row_loc, tri_xs, CUADMM_TRI_ARGS);
+}
+
+// Small subtrees (at most kWarpSubRows unknowns; tens of thousands of them in a chain-structured
+// relaxation): one WARP per subtree, __syncwarp between levels, so that an SM keeps 64 of them in
+// flight instead of a handful of mostly idle CTAs.
+__global__ void __launch_bounds__(kTriThreads) tri_subtree_warp_kernel(int64_t first, int64_t count,
+        const int64_t* __restrict__ sub_off, const int64_t* __restrict__ sub_lvl_ptr, const int32_t* __restrict__ dep_loc,
+        const int32_t* __restrict__ row_loc, CUADMM_TRI_PARAMS) {
+    if (done_flag && *done_flag) return;
+    __shared__ double xs_w[kTriThreads / 32][kWarpSubRows];
+    const int warp = threadIdx.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * (kTriThreads / 32) + warp;
+    if (t >= count) return;
+    const int64_t base = sub_off[first + t];
+    const int nl = (int)(sub_off[first + t + 1] - base) - 1;
+    tri_level_loop<1, true>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, 0, dep_loc, row_loc, xs_w[warp], CUADMM_TRI_ARGS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed subtrees.  The x-independent data of a subtree (structure + values of its rows, already in
+// level order) is laid out on the host as a stream of fixed-size CHUNKS, which one thread moves
+// global -> shared with 1-D TMA bulk copies (cp.async.bulk + mbarrier) kPkRing chunks ahead of the
+// warps that consume them.  The unknowns live in shared memory for the whole kernel, so a level
+// costs one __syncthreads plus shared-memory traffic: no global load sits on the critical path.
+//
+// chunk:  u16 nseg, u16 nslots, u16 seg_end[nseg], u16 rec_off[nslots] (8-byte units), records...
+//         a segment = consecutive slots of one level; every segment ends with a barrier.
+// record: i32 ne, i32 is_long, i32 uloc[8], u16 start[8], u16 len[8], f64 inv_diag[8], f64 val[ne], u16 idx[ne]
+//         (8 short rows x 4 lanes, or one long row x 32 lanes; idx = shared-memory index of the dependency)
+// Dependencies OUTSIDE the subtree are final when the kernel starts; the prologue folds them into
+// the right-hand side:  xs[loc] = rhs[u] - sum_ext val * x[dep].
+static constexpr int kPkChunk = 8192;
+static constexpr int kPkRing = 5;
+static constexpr int kPkThreads = 512;
+static constexpr int kPkRecHeader = 8 + 32 + 16 + 16 + 64;
+static constexpr int kPkMaxRowEntries = 768;
+static constexpr int kPkMaxRows = 23000;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void pk_fetch(unsigned char* dst, const unsigned char* src, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(kPkChunk) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(kPkChunk), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void pk_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ void pk_record(const unsigned char* rec, int lane, double* xs) {
+    const int32_t* hdr = reinterpret_cast<const int32_t*>(rec);
+    const int ne = hdr[0];
+    const bool is_long = hdr[1] != 0;
+    const int32_t* uloc = hdr + 2;
+    const uint16_t* start = reinterpret_cast<const uint16_t*>(rec + 40);
+    const uint16_t* len = start + 8;
+    const double* invd = reinterpret_cast<const double*>(rec + 72);
+    const double* val = invd + 8;
+    const uint16_t* idx = reinterpret_cast<const uint16_t*>(val + ne);
+    const int r = is_long ? 0 : (lane >> 2);
+    const int j = is_long ? lane : (lane & 3);
+    const int step = is_long ? 32 : 4;
+    const int ul = uloc[r];
+    double acc = 0.0;
+    if (ul >= 0) {
+        const int st = start[r], ln = len[r];
+        for (int k = j; k < ln; k += step) acc = fma(val[st + k], xs[idx[st + k]], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (is_long) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    }
+    if (ul >= 0 && j == 0) xs[ul] = (xs[ul] - acc) * invd[r];
+}
+
+__global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* __restrict__ chunk_off,
+        const int64_t* __restrict__ row_off, const unsigned char* __restrict__ stream, const int32_t* __restrict__ prow_u,
+        const int64_t* __restrict__ ext_ptr, const int32_t* __restrict__ ext_dep, const double* __restrict__ ext_val,
+        const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter,
+        const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    extern __shared__ __align__(128) unsigned char pk_smem[];
+    unsigned char* ring = pk_smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pk_smem + kPkRing * kPkChunk);
+    double* xs = reinterpret_cast<double*>(pk_smem + kPkRing * kPkChunk + 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kPkThreads / 32;
+    const int64_t c0 = chunk_off[blockIdx.x];
+    const int nc = (int)(chunk_off[blockIdx.x + 1] - c0);
+    const int64_t r0 = row_off[blockIdx.x];
+    const int nr = (int)(row_off[blockIdx.x + 1] - r0);
+    const unsigned char* src = stream + c0 * kPkChunk;
+    if (tid == 0) {
+        for (int i = 0; i < kPkRing; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < kPkRing && i < nc; ++i) pk_fetch(ring + i * kPkChunk, src + (int64_t)i * kPkChunk, bars + i);
+    }
+    // prologue: right-hand side minus the contributions of the (final) unknowns outside the subtree
+    for (int loc = tid; loc < nr; loc += kPkThreads) {
+        const int64_t g = r0 + loc;
+        const int32_t u = prow_u[g];
+        double acc = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
+        if (ext_ptr)
+            for (int64_t p = ext_ptr[g]; p < ext_ptr[g + 1]; ++p) acc = fma(-ext_val[p], x[ext_dep[p]], acc);
+        xs[loc] = acc;
+    }
+    __syncthreads();     // xs ready, barriers initialised
+    for (int c = 0; c < nc; ++c) {
+        const int b = c % kPkRing;
+        pk_wait(bars + b, (uint32_t)((c / kPkRing) & 1));
+        const unsigned char* chunk = ring + b * kPkChunk;
+        const uint16_t* dir = reinterpret_cast<const uint16_t*>(chunk);
+        const int nseg = dir[0];
+        const uint16_t* seg_end = dir + 2;
+        const uint16_t* rec_off = seg_end + nseg;
+        int sb = 0;
+        for (int g = 0; g < nseg; ++g) {
+            const int se = seg_end[g];
+            for (int sl = sb + warp; sl < se; sl += NW) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
+            __syncthreads();
+            sb = se;
+        }
+        // every thread is past its last read of this ring buffer: refill it
+        if (tid == 0 && c + kPkRing < nc) pk_fetch(ring + b * kPkChunk, src + (int64_t)(c + kPkRing) * kPkChunk, bars + b);
+    }
+    for (int loc = tid; loc < nr; loc += kPkThreads) {
+        const int32_t u = prow_u[r0 + loc];
+        const double r = xs[loc];
+        x[u] = r;
+        if (out_scatter) out_scatter[out_perm[u]] = r;
+    }
 }
 
 // dense tail: out[i] = sum_j T[i, j] * in[j] for a row-major r x r matrix of which only the
@@ -169,17 +352,47 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
     }
 }
 
-static void launch_subtrees(const TriSweep& S, const double* rhs, const int32_t* gather, double* x,
-                            double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
-    if (S.n_sub == 0) return;
-    tri_subtree_kernel<<<(unsigned)S.n_sub, kTriThreads, 0, st>>>(S.sub_off.p, S.sub_lvl_ptr.p, S.slot_rows.p, S.slot_info.p,
-        S.ptr.p, S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
+// the CTA-per-subtree kernel on `st`, the warp-per-subtree kernel concurrently on `side` (fork/join by events)
+static int launch_subtrees(const TriSweep& S, const double* rhs, const int32_t* gather, double* x, double* out_scatter,
+                           const int32_t* out_perm, const int* done, cudaStream_t st, const SweepStreams& ss) {
+    int launches = 0;
+    const bool both = (S.n_sub_cta > 0 || S.n_sub_pack > 0) && S.n_sub_warp > 0;
+    cudaStream_t wst = st;
+    if (both) {
+        CUADMM_CUDA(cudaEventRecord(ss.fork, st));
+        CUADMM_CUDA(cudaStreamWaitEvent(ss.side, ss.fork, 0));
+        wst = ss.side;
+    }
+    if (S.n_sub_warp > 0) {
+        const int wpb = kTriThreads / 32;
+        tri_subtree_warp_kernel<<<(unsigned)((S.n_sub_warp + wpb - 1) / wpb), kTriThreads, 0, wst>>>(S.n_sub_cta, S.n_sub_warp,
+            S.sub_off.p, S.sub_lvl_ptr.p, S.dep_loc.p, S.row_loc.p, S.slot_rows.p, S.slot_info.p, S.ptr.p, S.dep.p, S.val.p,
+            S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
+        ++launches;
+    }
+    if (S.n_sub_pack > 0) {
+        tri_packed_kernel<<<(unsigned)S.n_sub_pack, kPkThreads, S.pk_smem, st>>>(S.pk_chunk_off.p, S.pk_row_off.p, S.pk_stream.p,
+            S.pk_prow_u.p, S.pk_has_ext ? S.pk_ext_ptr.p : nullptr, S.pk_ext_dep.p, S.pk_ext_val.p, rhs, gather, x, out_scatter,
+            out_perm, done);
+        ++launches;
+    }
+    if (S.n_sub_cta > 0) {
+        tri_subtree_kernel<<<(unsigned)S.n_sub_cta, kTriThreads, S.sub_smem, st>>>(S.sub_off.p, S.sub_lvl_ptr.p, S.dep_loc.p,
+            S.row_loc.p, S.slot_rows.p, S.slot_info.p, S.ptr.p, S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, out_scatter,
+            out_perm, done);
+        ++launches;
+    }
+    if (both) {
+        CUADMM_CUDA(cudaEventRecord(ss.join, ss.side));
+        CUADMM_CUDA(cudaStreamWaitEvent(st, ss.join, 0));
+    }
+    return launches;
 }
 
 static int launch_sweep(const TriSweep& S, const double* rhs, const int32_t* gather, double* x,
-                        double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st) {
+                        double* out_scatter, const int32_t* out_perm, const int* done, cudaStream_t st, const SweepStreams& ss) {
     int launches = 0;
-    if (S.subtrees_first && S.n_sub) { launch_subtrees(S, rhs, gather, x, out_scatter, out_perm, done, st); ++launches; }
+    if (S.subtrees_first && S.n_sub) launches += launch_subtrees(S, rhs, gather, x, out_scatter, out_perm, done, st, ss);
     for (const TriSweep::Phase& ph : S.phases) {
         if (ph.narrow) {
             tri_narrow_kernel<<<1, kNarrowThreads, 0, st>>>(ph.level0, ph.level1, S.level_ptr.p, S.slot_rows.p, S.slot_info.p,
@@ -192,7 +405,7 @@ static int launch_sweep(const TriSweep& S, const double* rhs, const int32_t* gat
         }
         ++launches;
     }
-    if (!S.subtrees_first && S.n_sub) { launch_subtrees(S, rhs, gather, x, out_scatter, out_perm, done, st); ++launches; }
+    if (!S.subtrees_first && S.n_sub) launches += launch_subtrees(S, rhs, gather, x, out_scatter, out_perm, done, st, ss);
     CUADMM_CUDA(cudaGetLastError());
     return launches;
 }
@@ -231,6 +444,124 @@ static int64_t emit_level_slots(const HostSweep& H, std::vector<int32_t>& rows, 
     return cnt;
 }
 
+// host side of tri_packed_kernel: chunk streams, row lists and the external (out-of-subtree) entries
+static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std::vector<int32_t>>& members,
+                          const std::vector<int32_t>& level, const std::vector<int32_t>& depth, const std::vector<int>& kind) {
+    struct Packed { std::vector<unsigned char> bytes; int32_t t; };
+    std::vector<Packed> packs;
+    std::vector<int32_t> loc(H.n, -1);
+    for (int64_t t = 0; t < H.n_sub; ++t) {
+        if (kind[t] != 2) continue;
+        const std::vector<int32_t>& rows = members[t];
+        for (size_t q = 0; q < rows.size(); ++q) loc[rows[q]] = (int32_t)q;
+        std::vector<std::vector<int32_t>> by_level(depth[t]);
+        for (int32_t u : rows) by_level[level[u]].push_back(u);
+        Packed P; P.t = (int32_t)t;
+        // open chunk state
+        std::vector<uint16_t> seg_end, rec_rel;      // rec_rel: record offsets (bytes) inside the records area
+        std::vector<unsigned char> recs;
+        auto dir_bytes = [](size_t nseg, size_t nslots) { return (4 + 2 * nseg + 2 * nslots + 7) / 8 * 8; };
+        auto close_chunk = [&]() {
+            if (rec_rel.empty()) return;
+            seg_end.push_back((uint16_t)rec_rel.size());
+            const size_t db = dir_bytes(seg_end.size(), rec_rel.size());
+            std::vector<unsigned char> chunk(kPkChunk, 0);
+            uint16_t* dir = reinterpret_cast<uint16_t*>(chunk.data());
+            dir[0] = (uint16_t)seg_end.size(); dir[1] = (uint16_t)rec_rel.size();
+            for (size_t i = 0; i < seg_end.size(); ++i) dir[2 + i] = seg_end[i];
+            for (size_t i = 0; i < rec_rel.size(); ++i) dir[2 + seg_end.size() + i] = (uint16_t)((db + rec_rel[i]) / 8);
+            CUADMM_REQUIRE(db + recs.size() <= (size_t)kPkChunk, "internal: packed chunk overflow");
+            std::copy(recs.begin(), recs.end(), chunk.begin() + db);
+            P.bytes.insert(P.bytes.end(), chunk.begin(), chunk.end());
+            seg_end.clear(); rec_rel.clear(); recs.clear();
+        };
+        auto add_record = [&](const std::vector<unsigned char>& rec, bool new_level) {
+            size_t nseg = seg_end.size() + 1 + ((new_level && !rec_rel.empty()) ? 1 : 0);
+            if (dir_bytes(nseg, rec_rel.size() + 1) + recs.size() + rec.size() > (size_t)kPkChunk) close_chunk();
+            if (new_level && !rec_rel.empty()) seg_end.push_back((uint16_t)rec_rel.size());
+            rec_rel.push_back((uint16_t)recs.size());
+            recs.insert(recs.end(), rec.begin(), rec.end());
+        };
+        auto make_record = [&](const int32_t* us, int nrows, bool is_long) {
+            int ne = 0;
+            std::vector<int32_t> uloc(8, -1);
+            std::vector<uint16_t> start(8, 0), len(8, 0);
+            std::vector<double> invd(8, 0.0), val;
+            std::vector<uint16_t> idx;
+            for (int r = 0; r < nrows; ++r) {
+                const int32_t u = us[r];
+                uloc[r] = loc[u]; start[r] = (uint16_t)val.size(); invd[r] = H.inv_diag[u];
+                for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
+                    if (H.sub[H.dep[p]] == H.sub[u]) { val.push_back(H.val[p]); idx.push_back((uint16_t)loc[H.dep[p]]); }
+                len[r] = (uint16_t)(val.size() - start[r]);
+            }
+            ne = (int)val.size();
+            std::vector<unsigned char> rec(kPkRecHeader + 8 * (size_t)ne + (2 * (size_t)ne + 7) / 8 * 8, 0);
+            int32_t* hdr = reinterpret_cast<int32_t*>(rec.data());
+            hdr[0] = ne; hdr[1] = is_long ? 1 : 0;
+            std::copy(uloc.begin(), uloc.end(), hdr + 2);
+            std::copy(start.begin(), start.end(), reinterpret_cast<uint16_t*>(rec.data() + 40));
+            std::copy(len.begin(), len.end(), reinterpret_cast<uint16_t*>(rec.data() + 56));
+            std::copy(invd.begin(), invd.end(), reinterpret_cast<double*>(rec.data() + 72));
+            if (ne) {
+                std::copy(val.begin(), val.end(), reinterpret_cast<double*>(rec.data() + kPkRecHeader));
+                std::copy(idx.begin(), idx.end(), reinterpret_cast<uint16_t*>(rec.data() + kPkRecHeader + 8 * (size_t)ne));
+            }
+            return rec;
+        };
+        for (int l = 0; l < depth[t]; ++l) {
+            std::vector<int32_t> longs, shorts;
+            for (int32_t u : by_level[l]) {
+                int cnt = 0;
+                for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) cnt += (H.sub[H.dep[p]] == H.sub[u]) ? 1 : 0;
+                (cnt > kLongRowNnz ? longs : shorts).push_back(u);
+            }
+            bool first = true;
+            for (int32_t u : longs) { add_record(make_record(&u, 1, true), first); first = false; }
+            for (size_t q = 0; q < shorts.size(); q += 8) {
+                add_record(make_record(shorts.data() + q, (int)std::min<size_t>(8, shorts.size() - q), false), first);
+                first = false;
+            }
+        }
+        close_chunk();
+        packs.push_back(std::move(P));
+    }
+    S.n_sub_pack = (int64_t)packs.size();
+    S.pk_smem = 0;
+    if (packs.empty()) return;
+    std::stable_sort(packs.begin(), packs.end(), [](const Packed& a, const Packed& b) { return a.bytes.size() > b.bytes.size(); });
+    std::vector<int64_t> chunk_off(1, 0), row_off(1, 0), ext_ptr(1, 0);
+    std::vector<int32_t> prow_u, ext_dep;
+    std::vector<double> ext_val;
+    std::vector<unsigned char> stream;
+    size_t total = 0;
+    for (const Packed& P : packs) total += P.bytes.size();
+    stream.reserve(total);
+    int64_t max_rows = 0;
+    for (const Packed& P : packs) {
+        stream.insert(stream.end(), P.bytes.begin(), P.bytes.end());
+        chunk_off.push_back((int64_t)(stream.size() / kPkChunk));
+        for (int32_t u : members[P.t]) {
+            prow_u.push_back(u);
+            for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
+                if (H.sub[H.dep[p]] != H.sub[u]) { ext_dep.push_back(H.dep[p]); ext_val.push_back(H.val[p]); }
+            ext_ptr.push_back((int64_t)ext_dep.size());
+        }
+        row_off.push_back((int64_t)prow_u.size());
+        max_rows = std::max<int64_t>(max_rows, (int64_t)members[P.t].size());
+    }
+    S.pk_has_ext = !ext_dep.empty();
+    if (ext_dep.empty()) { ext_dep.push_back(0); ext_val.push_back(0.0); }
+    S.pk_stream.upload(stream); S.pk_chunk_off.upload(chunk_off); S.pk_row_off.upload(row_off);
+    S.pk_prow_u.upload(prow_u); S.pk_ext_ptr.upload(ext_ptr); S.pk_ext_dep.upload(ext_dep); S.pk_ext_val.upload(ext_val);
+    S.pk_smem = (size_t)kPkRing * kPkChunk + 64 + sizeof(double) * (size_t)max_rows;
+    CUADMM_CUDA(cudaFuncSetAttribute((const void*)tri_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.pk_smem));
+    if (getenv("CUADMM_YSOLVE_VERBOSE"))
+        fprintf(stderr, "[ysolve] packed: %lld subtrees, %lld rows, %lld chunks (largest %lld), %lld external entries, smem %zu\n",
+                (long long)packs.size(), (long long)prow_u.size(), (long long)chunk_off.back(),
+                (long long)(packs[0].bytes.size() / kPkChunk), (long long)ext_ptr.back(), S.pk_smem);
+}
+
 static void upload_sweep(const HostSweep& H, TriSweep& S) {
     S.n_unknowns = (int64_t)H.order.size();
     S.nnz = (int64_t)H.dep.size();
@@ -256,7 +587,34 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
     }
     std::vector<int32_t> sub_order(H.n_sub);
     std::iota(sub_order.begin(), sub_order.end(), 0);
-    std::stable_sort(sub_order.begin(), sub_order.end(), [&](int32_t a, int32_t b) { return depth[a] > depth[b]; });
+    // three groups: packed (TMA-streamed CTA per subtree), generic CTA per subtree (fallback), warp per subtree
+    bool use_packed = true;
+    if (const char* e = getenv("CUADMM_SWEEP_PACKED")) use_packed = atoi(e) != 0;
+    std::vector<int32_t> loc_cnt(H.n, 0);
+    for (int32_t u : H.order) if (H.sub[u] >= 0)
+        for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) loc_cnt[u] += (H.sub[H.dep[p]] == H.sub[u]) ? 1 : 0;
+    std::vector<int> kind(H.n_sub, 0);          // 0 generic, 1 warp, 2 packed
+    for (int64_t t = 0; t < H.n_sub; ++t) {
+        const int64_t rows = (int64_t)members[t].size();
+        if (rows <= kWarpSubRows) { kind[t] = 1; continue; }
+        int32_t longest = 0;
+        for (int32_t u : members[t]) longest = std::max(longest, loc_cnt[u]);
+        if (use_packed && rows <= kPkMaxRows && longest <= kPkMaxRowEntries) kind[t] = 2;
+    }
+    auto small = [&](int32_t t) { return kind[t] == 1; };
+    {
+        std::vector<int32_t> keep;
+        for (int32_t t : sub_order) if (kind[t] != 2) keep.push_back(t);
+        sub_order.swap(keep);
+    }
+    std::stable_sort(sub_order.begin(), sub_order.end(), [&](int32_t a, int32_t b) {
+        if (small(a) != small(b)) return small(b);
+        return depth[a] > depth[b];
+    });
+    S.n_sub_warp = 0;
+    for (int32_t t : sub_order) S.n_sub_warp += small(t) ? 1 : 0;
+    S.n_sub_cta = (int64_t)sub_order.size() - S.n_sub_warp;
+    pack_subtrees(H, S, members, level, depth, kind);
     std::vector<int64_t> sub_off(1, 0), sub_lvl_ptr;
     int max_sub_depth = 0;
     for (int32_t t : sub_order) {
@@ -272,6 +630,41 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
     }
     S.n_sub = H.n_sub;
     S.sub_depth = max_sub_depth;
+    // shared-memory residency: local index of every subtree unknown, and per entry the local index of
+    // its dependency when that lives in the same subtree (-1: read the global vector)
+    std::vector<int32_t> row_loc(H.n, -1), dep_loc(std::max<size_t>(H.dep.size(), 1), -1);
+    int64_t max_rows = 0;
+    for (int64_t t = 0; t < H.n_sub; ++t) {
+        if (kind[t] == 2) continue;
+        for (size_t q = 0; q < members[t].size(); ++q) row_loc[members[t][q]] = (int32_t)q;
+        if (!small((int32_t)t)) max_rows = std::max<int64_t>(max_rows, (int64_t)members[t].size());
+    }
+    for (int32_t u : H.order) if (H.sub[u] >= 0 && kind[H.sub[u]] != 2)
+        for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) if (H.sub[H.dep[p]] == H.sub[u]) dep_loc[p] = row_loc[H.dep[p]];
+    S.row_loc.upload(row_loc); S.dep_loc.upload(dep_loc);
+    if (getenv("CUADMM_YSOLVE_VERBOSE")) {
+        int64_t rows = 0, lv = 0;
+        for (int64_t t = 0; t < H.n_sub; ++t) { rows += (int64_t)members[t].size(); lv += depth[t]; }
+        fprintf(stderr, "[ysolve] %s sweep: %lld subtrees, %lld rows, %lld slots, max rows %lld, sum depth %lld; deepest:",
+                H.subtrees_first ? "fwd" : "bwd", (long long)H.n_sub, (long long)rows, (long long)slot_info.size(),
+                (long long)max_rows, (long long)lv);
+        for (size_t q = 0; q < std::min<size_t>(8, sub_order.size()); ++q)
+            fprintf(stderr, " %d/%zu", depth[sub_order[q]], members[sub_order[q]].size());
+        fprintf(stderr, "\n");
+        const int64_t edges[] = {8, 32, 128, 256, 512, 1024, 2048, 4096, 1 << 30};
+        for (int b = 0; b < 9; ++b) {
+            int64_t cnt = 0, r = 0, dsum = 0; int dmax = 0;
+            for (int64_t t = 0; t < H.n_sub; ++t) {
+                const int64_t sz = (int64_t)members[t].size();
+                if (sz <= edges[b] && (b == 0 || sz > edges[b - 1])) { ++cnt; r += sz; dsum += depth[t]; dmax = std::max(dmax, depth[t]); }
+            }
+            fprintf(stderr, "[ysolve]   rows<=%lld: %lld subtrees, %lld rows, sum depth %lld, max depth %d\n",
+                    (long long)edges[b], (long long)cnt, (long long)r, (long long)dsum, dmax);
+        }
+    }
+    S.sub_smem = sizeof(double) * (size_t)max_rows;
+    if (S.sub_smem > 48 * 1024)
+        CUADMM_CUDA(cudaFuncSetAttribute((const void*)tri_subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.sub_smem));
     // ---- top part: global levels, wide levels one launch each, narrow runs in one CTA
     int maxlev = -1;
     for (int32_t u : H.order) if (H.sub[u] < 0) maxlev = std::max(maxlev, (int)level[u]);
@@ -317,9 +710,10 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
 static int64_t choose_subtrees(const CholFactor& F, int64_t n_lead, std::vector<int32_t>& sub) {
     const int64_t n = F.n;
     sub.assign(n, -1);
-    int64_t cap = 32768;
+    int64_t cap = 12288;          // rows per subtree: its unknowns live in shared memory (96 KB + the chunk ring)
     if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_CAP")) cap = atoll(e);
     if (cap <= 0) return 0;
+    cap = std::min<int64_t>(cap, 28000);   // 227 KB of shared memory
     int64_t min_size = 2;         // (measured: peeling small subtrees off into extra top levels costs more than their CTAs)
     if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_MIN")) min_size = atoll(e);
     std::vector<int64_t> size(n, 1);
@@ -464,7 +858,11 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         Y->n_deficient += tail_def;
         Y->tail_tmp.alloc(n_tail);
     }
-    Y->launches_per_solve = (int)(Y->fwd.phases.size() + Y->bwd.phases.size()) + (n_tail > 0 ? 2 : 0) + (n_sub > 0 ? 2 : 0);
+    Y->launches_per_solve = (int)(Y->fwd.phases.size() + Y->bwd.phases.size()) + (n_tail > 0 ? 2 : 0) +
+                            (Y->fwd.n_sub_cta > 0 ? 2 : 0) + (Y->fwd.n_sub_warp > 0 ? 2 : 0) + (Y->fwd.n_sub_pack > 0 ? 2 : 0);
+    CUADMM_CUDA(cudaStreamCreateWithFlags(&Y->streams.side, cudaStreamNonBlocking));
+    CUADMM_CUDA(cudaEventCreateWithFlags(&Y->streams.fork, cudaEventDisableTiming));
+    CUADMM_CUDA(cudaEventCreateWithFlags(&Y->streams.join, cudaEventDisableTiming));
     Y->alg_bytes = 2 * (12 * Y->nnz_L + 8 * m) + 24 * m;
     CUADMM_CUDA(cudaDeviceSynchronize());
     return Y.release();
@@ -474,10 +872,16 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
 
 using namespace cuadmm;
 
+cuadmm_ysolve_s::~cuadmm_ysolve_s() {
+    if (streams.fork) cudaEventDestroy(streams.fork);
+    if (streams.join) cudaEventDestroy(streams.join);
+    if (streams.side) cudaStreamDestroy(streams.side);
+}
+
 void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st) {
     if (m == 0) return;
     // forward: z = L11^-1 P rhs (lead), z_tail = P rhs - L21 z_lead
-    launch_sweep(fwd, d_rhs_, perm.p, z.p, nullptr, nullptr, done_flag, st);
+    launch_sweep(fwd, d_rhs_, perm.p, z.p, nullptr, nullptr, done_flag, st, streams);
     if (n_tail > 0) {
         const int blocks = (int)((n_tail + 7) / 8);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
@@ -486,7 +890,7 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
         CUADMM_CUDA(cudaGetLastError());
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y
-    launch_sweep(bwd, z.p, nullptr, x.p, d_y_, perm.p, done_flag, st);
+    launch_sweep(bwd, z.p, nullptr, x.p, d_y_, perm.p, done_flag, st, streams);
 }
 
 extern "C" {

@@ -26,9 +26,25 @@ struct TriSweep {
     int levels = 0;               // levels of the top part
     // subtree part: CTA t walks levels [sub_off[t], sub_off[t+1]-1) of sub_lvl_ptr (slot offsets)
     DevBuf<int64_t> sub_off, sub_lvl_ptr;
-    int64_t n_sub = 0;
+    DevBuf<int32_t> dep_loc, row_loc;   // shared-memory indices (see ysolve.cu)
+    size_t sub_smem = 0;
+    int64_t n_sub = 0, n_sub_cta = 0, n_sub_warp = 0;   // CTA-per-subtree group first, warp-per-subtree group after
+    // packed subtrees (TMA-streamed, see tri_packed_kernel)
+    int64_t n_sub_pack = 0;
+    DevBuf<unsigned char> pk_stream;
+    DevBuf<int64_t> pk_chunk_off, pk_row_off, pk_ext_ptr;
+    DevBuf<int32_t> pk_prow_u, pk_ext_dep;
+    DevBuf<double> pk_ext_val;
+    size_t pk_smem = 0;
+    bool pk_has_ext = false;
     int sub_depth = 0;
     bool subtrees_first = true;
+};
+
+// side stream + events to run the two subtree kernels of a sweep concurrently
+struct SweepStreams {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 };
 
 }  // namespace cuadmm
@@ -47,6 +63,8 @@ struct cuadmm_ysolve_s {
     cuadmm::DevBuf<double> d_rhs, d_y; // staging for the host entry
     std::vector<int32_t> h_perm;
     const int* done_flag = nullptr;
+    cuadmm::SweepStreams streams;
+    ~cuadmm_ysolve_s();
     int launches_per_solve = 0;
     int64_t alg_bytes = 0;
     void solve(const double* d_rhs, double* d_y, cudaStream_t stream);
