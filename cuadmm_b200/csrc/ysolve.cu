@@ -20,7 +20,6 @@ static constexpr int kTriThreads = 256;
 static constexpr int kLongRowNnz = 24;     // rows with more dependencies get a whole warp
 static constexpr int kNarrowSlots = 160;   // levels with at most this many warp-slots run inside one CTA
 static constexpr int kNarrowThreads = 1024;
-static constexpr int kWarpSubRows = 32;     // subtrees up to this many unknowns are solved by one warp
 
 // Work of a triangular sweep is cut into warp-slots: a slot is either 8 short rows (4 lanes each) or
 // 1 long row (32 lanes), all of one dependency level.  The levels are grouped into phases:
@@ -36,44 +35,37 @@ static constexpr int kWarpSubRows = 32;     // subtrees up to this many unknowns
 // this turns a chain of five dependent global loads per level into one.
 struct SlotWork {
     static constexpr int K = 4;        // entries per lane kept in registers
-    int32_t u, uloc; int is_long;
+    int32_t u; int is_long;
     double rv, invd;
     int64_t p, p1; int step;
-    int32_t d[K], dl[K]; double v[K];
+    int32_t d[K]; double v[K];
 
     __device__ __forceinline__ void load(int64_t s, int lane, const int32_t* __restrict__ slot_rows,
             const int32_t* __restrict__ slot_info, const int64_t* __restrict__ ptr, const int32_t* __restrict__ dep,
             const double* __restrict__ val, const double* __restrict__ inv_diag, const double* __restrict__ rhs,
-            const int32_t* __restrict__ rhs_gather, const int32_t* __restrict__ dep_loc, const int32_t* __restrict__ row_loc) {
+            const int32_t* __restrict__ rhs_gather) {
         is_long = slot_info[s] >> 30;
         u = slot_rows[8 * s + (is_long ? 0 : (lane >> 2))];
         step = is_long ? 32 : 4;
-        p = 0; p1 = 0; rv = 0.0; invd = 0.0; uloc = -1;
+        p = 0; p1 = 0; rv = 0.0; invd = 0.0;
         if (u >= 0) {
             p = ptr[u] + (is_long ? lane : (lane & 3));
             p1 = ptr[u + 1];
             invd = inv_diag[u];
             rv = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
-            if (row_loc) uloc = row_loc[u];
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int64_t q = p + (int64_t)k * step;
-            if (q < p1) { d[k] = dep[q]; v[k] = val[q]; dl[k] = dep_loc ? dep_loc[q] : -1; }
-            else { d[k] = -1; v[k] = 0.0; dl[k] = -1; }
+            if (q < p1) { d[k] = dep[q]; v[k] = val[q]; } else { d[k] = -1; v[k] = 0.0; }
         }
     }
-    // xs: the subtree's unknowns in shared memory (null for the top-part kernels)
     __device__ __forceinline__ void finish(int lane, const int32_t* __restrict__ dep, const double* __restrict__ val,
-                                           const int32_t* __restrict__ dep_loc, double* x, double* xs,
-                                           double* out_scatter, const int32_t* __restrict__ out_perm) {
+                                           double* x, double* out_scatter, const int32_t* __restrict__ out_perm) {
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) if (d[k] >= 0) acc = fma(v[k], (xs && dl[k] >= 0) ? xs[dl[k]] : x[d[k]], acc);
-        for (int64_t q = p + (int64_t)K * step; q < p1; q += step) {
-            const int32_t l = (xs && dep_loc) ? dep_loc[q] : -1;
-            acc = fma(val[q], l >= 0 ? xs[l] : x[dep[q]], acc);
-        }
+        for (int k = 0; k < K; ++k) if (d[k] >= 0) acc = fma(v[k], x[d[k]], acc);
+        for (int64_t q = p + (int64_t)K * step; q < p1; q += step) acc = fma(val[q], x[dep[q]], acc);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         if (is_long) {
@@ -85,7 +77,6 @@ struct SlotWork {
         if (writer) {
             const double r = (rv - acc) * invd;
             x[u] = r;
-            if (xs && uloc >= 0) xs[uloc] = r;
             if (out_scatter) out_scatter[out_perm[u]] = r;
         }
     }
@@ -96,113 +87,65 @@ struct SlotWork {
     const int32_t* __restrict__ dep, const double* __restrict__ val, const double* __restrict__ inv_diag,   \
     const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter, \
     const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag
-#define CUADMM_TRI_ARGS slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag
-#define CUADMM_TRI_LOAD(W, S) (W).load((S), lane, slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, dep_loc, row_loc)
-#define CUADMM_TRI_FINISH(W) (W).finish(lane, dep, val, dep_loc, x, xs, out_scatter, out_perm)
+#define CUADMM_TRI_LOAD(W, S) (W).load((S), lane, slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather)
+#define CUADMM_TRI_FINISH(W) (W).finish(lane, dep, val, x, out_scatter, out_perm)
 
 __global__ void __launch_bounds__(kTriThreads) tri_wide_kernel(int64_t slot0, int64_t slot1, CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
     const int lane = threadIdx.x & 31;
     const int64_t s = slot0 + (((int64_t)blockIdx.x * kTriThreads + threadIdx.x) >> 5);
     if (s >= slot1) return;
-    const int32_t* dep_loc = nullptr; const int32_t* row_loc = nullptr; double* xs = nullptr;
     SlotWork w;
     CUADMM_TRI_LOAD(w, s);
     CUADMM_TRI_FINISH(w);
 }
 
-// levels [level0, level1) of lvl_ptr inside one CTA of NW warps.  The x-independent part of a warp's
-// first slot is prefetched TWO levels ahead (two register sets), so that by the time a level starts
-// only the x values (shared memory for subtrees) are on the critical path.
-template <int NW, bool WARP>
+// levels [level0, level1) of lvl_ptr inside one CTA of NW warps; the first slot of the next level is
+// prefetched (static part) before the barrier of the current one
+template <int NW>
 __device__ __forceinline__ void tri_level_loop(const int64_t* __restrict__ lvl_ptr, int level0, int level1, int lane, int warp,
-        const int32_t* __restrict__ dep_loc, const int32_t* __restrict__ row_loc, double* xs, CUADMM_TRI_PARAMS) {
+        CUADMM_TRI_PARAMS) {
     (void)done_flag;
     if (level0 >= level1) return;
-    SlotWork w0, w1;
-    bool h0 = false, h1 = false;
-    {
-        const int64_t a = lvl_ptr[level0] + warp;
-        h0 = a < lvl_ptr[level0 + 1];
-        if (h0) CUADMM_TRI_LOAD(w0, a);
-        if (level0 + 1 < level1) {
-            const int64_t b = lvl_ptr[level0 + 1] + warp;
-            h1 = b < lvl_ptr[level0 + 2];
-            if (h1) CUADMM_TRI_LOAD(w1, b);
+    SlotWork w;
+    int64_t s0 = lvl_ptr[level0];
+    int64_t s1 = lvl_ptr[level0 + 1];
+    bool have = (s0 + warp) < s1;
+    if (have) CUADMM_TRI_LOAD(w, s0 + warp);
+    for (int l = level0; l < level1; ++l) {
+        if (have) {
+            CUADMM_TRI_FINISH(w);
+            for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
         }
-    }
-    for (int l = level0; l < level1; l += 2) {
-        // ---- level l (register set 0)
-        {
-            const int64_t s0 = lvl_ptr[l], s1 = lvl_ptr[l + 1];
-            if (h0) {
-                CUADMM_TRI_FINISH(w0);
-                for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
-            }
-            h0 = false;
-            if (l + 2 < level1) {
-                const int64_t a = lvl_ptr[l + 2] + warp;
-                h0 = a < lvl_ptr[l + 3];
-                if (h0) CUADMM_TRI_LOAD(w0, a);
-            }
-            if constexpr (WARP) __syncwarp(); else __syncthreads();   // orders this level's writes before the next level's reads
+        s0 = s1;
+        have = false;
+        if (l + 1 < level1) {
+            s1 = lvl_ptr[l + 2];
+            have = (s0 + warp) < s1;
+            if (have) CUADMM_TRI_LOAD(w, s0 + warp);
         }
-        if (l + 1 >= level1) break;
-        // ---- level l + 1 (register set 1)
-        {
-            const int64_t s0 = lvl_ptr[l + 1], s1 = lvl_ptr[l + 2];
-            if (h1) {
-                CUADMM_TRI_FINISH(w1);
-                for (int64_t s = s0 + warp + NW; s < s1; s += NW) { SlotWork t; CUADMM_TRI_LOAD(t, s); CUADMM_TRI_FINISH(t); }
-            }
-            h1 = false;
-            if (l + 3 < level1) {
-                const int64_t b = lvl_ptr[l + 3] + warp;
-                h1 = b < lvl_ptr[l + 4];
-                if (h1) CUADMM_TRI_LOAD(w1, b);
-            }
-            if constexpr (WARP) __syncwarp(); else __syncthreads();
-        }
+        __syncthreads();   // also makes this CTA's global writes visible to its own later loads
     }
 }
 
 __global__ void __launch_bounds__(kNarrowThreads) tri_narrow_kernel(int level0, int level1, const int64_t* __restrict__ level_ptr,
                                                                     CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
-    tri_level_loop<kNarrowThreads / 32, false>(level_ptr, level0, level1, threadIdx.x & 31, threadIdx.x >> 5,
-                                        nullptr, nullptr, nullptr, CUADMM_TRI_ARGS);
+    tri_level_loop<kNarrowThreads / 32>(level_ptr, level0, level1, threadIdx.x & 31, threadIdx.x >> 5,
+        slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag);
 }
 
 // Subtree parallelism: every CTA owns one subtree of the elimination tree (all of whose dependencies
-// are inside the subtree, or already final), keeps the subtree's unknowns in SHARED MEMORY and walks
-// the subtree's own levels with __syncthreads.  Thousands of independent deep chains (one per block
-// neighbourhood of a moment relaxation) thus cost ONE launch and depth x (shared-memory round trip)
-// instead of depth x (kernel boundary) or depth x (L2 round trip).
+// are inside the subtree, or already final), and walks the subtree's own levels with __syncthreads.
+// Thousands of independent deep chains (one per block neighbourhood of a moment relaxation) thus cost
+// ONE launch and depth x (one x-load latency) instead of depth x (kernel boundary).
 __global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t* __restrict__ sub_off,
-        const int64_t* __restrict__ sub_lvl_ptr, const int32_t* __restrict__ dep_loc, const int32_t* __restrict__ row_loc,
-        CUADMM_TRI_PARAMS) {
+        const int64_t* __restrict__ sub_lvl_ptr, CUADMM_TRI_PARAMS) {
     if (done_flag && *done_flag) return;
-    extern __shared__ double tri_xs[];
     const int64_t base = sub_off[blockIdx.x];
     const int nl = (int)(sub_off[blockIdx.x + 1] - base) - 1;
-    tri_level_loop<kTriThreads / 32, false>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, threadIdx.x >> 5,
-                                            dep_loc, row_loc, tri_xs, CUADMM_TRI_ARGS);
-}
-
-// Small subtrees (at most kWarpSubRows unknowns; tens of thousands of them in a chain-structured
-// relaxation): one WARP per subtree, __syncwarp between levels, so that an SM keeps 64 of them in
-// flight instead of a handful of mostly idle CTAs.
-__global__ void __launch_bounds__(kTriThreads) tri_subtree_warp_kernel(int64_t first, int64_t count,
-        const int64_t* __restrict__ sub_off, const int64_t* __restrict__ sub_lvl_ptr, const int32_t* __restrict__ dep_loc,
-        const int32_t* __restrict__ row_loc, CUADMM_TRI_PARAMS) {
-    if (done_flag && *done_flag) return;
-    __shared__ double xs_w[kTriThreads / 32][kWarpSubRows];
-    const int warp = threadIdx.x >> 5;
-    const int64_t t = (int64_t)blockIdx.x * (kTriThreads / 32) + warp;
-    if (t >= count) return;
-    const int64_t base = sub_off[first + t];
-    const int nl = (int)(sub_off[first + t + 1] - base) - 1;
-    tri_level_loop<1, true>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, 0, dep_loc, row_loc, xs_w[warp], CUADMM_TRI_ARGS);
+    tri_level_loop<kTriThreads / 32>(sub_lvl_ptr + base, 0, nl, threadIdx.x & 31, threadIdx.x >> 5,
+        slot_rows, slot_info, ptr, dep, val, inv_diag, rhs, rhs_gather, x, out_scatter, out_perm, done_flag);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,18 +213,47 @@ __device__ __forceinline__ void pk_record(const unsigned char* rec, int lane, do
     if (ul >= 0 && j == 0) xs[ul] = (xs[ul] - acc) * invd[r];
 }
 
+// w[g] = rhs[src[g]] - sum over the row's dependencies OUTSIDE its subtree (all final by now) of
+// val * x[dep]: one thread per packed row, so the subtree kernels start from a coalesced read.
+__global__ void __launch_bounds__(256) pk_gather_kernel(int64_t n_rows, const int32_t* __restrict__ prow_src,
+        const int64_t* __restrict__ ext_ptr, const int32_t* __restrict__ ext_dep, const double* __restrict__ ext_val,
+        const double* __restrict__ rhs, const double* __restrict__ x, double* __restrict__ w,
+        const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_rows) return;
+    double acc = rhs[prow_src[g]];
+    if (ext_ptr)
+        for (int64_t p = ext_ptr[g]; p < ext_ptr[g + 1]; ++p) acc = fma(-ext_val[p], x[ext_dep[p]], acc);
+    w[g] = acc;
+}
+
+// walk the segments of one chunk (resident in shared memory) with NW warps; WARP = the chunk belongs to one warp
+template <int NW, bool WARP>
+__device__ __forceinline__ void pk_chunk(const unsigned char* chunk, int lane, int warp, double* xs) {
+    const uint16_t* dir = reinterpret_cast<const uint16_t*>(chunk);
+    const int nseg = dir[0];
+    const uint16_t* seg_end = dir + 2;
+    const uint16_t* rec_off = seg_end + nseg;
+    int sb = 0;
+    for (int g = 0; g < nseg; ++g) {
+        const int se = seg_end[g];
+        for (int sl = sb + warp; sl < se; sl += NW) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
+        if constexpr (WARP) __syncwarp(); else __syncthreads();
+        sb = se;
+    }
+}
+
 __global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* __restrict__ chunk_off,
         const int64_t* __restrict__ row_off, const unsigned char* __restrict__ stream, const int32_t* __restrict__ prow_u,
-        const int64_t* __restrict__ ext_ptr, const int32_t* __restrict__ ext_dep, const double* __restrict__ ext_val,
-        const double* __restrict__ rhs, const int32_t* __restrict__ rhs_gather, double* x, double* out_scatter,
-        const int32_t* __restrict__ out_perm, const int* __restrict__ done_flag) {
+        const int32_t* __restrict__ prow_out, const double* __restrict__ w, double* x, double* out_scatter,
+        const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
     extern __shared__ __align__(128) unsigned char pk_smem[];
     unsigned char* ring = pk_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(pk_smem + kPkRing * kPkChunk);
     double* xs = reinterpret_cast<double*>(pk_smem + kPkRing * kPkChunk + 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kPkThreads / 32;
     const int64_t c0 = chunk_off[blockIdx.x];
     const int nc = (int)(chunk_off[blockIdx.x + 1] - c0);
     const int64_t r0 = row_off[blockIdx.x];
@@ -294,39 +266,61 @@ __global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* _
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int i = 0; i < kPkRing && i < nc; ++i) pk_fetch(ring + i * kPkChunk, src + (int64_t)i * kPkChunk, bars + i);
     }
-    // prologue: right-hand side minus the contributions of the (final) unknowns outside the subtree
-    for (int loc = tid; loc < nr; loc += kPkThreads) {
-        const int64_t g = r0 + loc;
-        const int32_t u = prow_u[g];
-        double acc = rhs_gather ? rhs[rhs_gather[u]] : rhs[u];
-        if (ext_ptr)
-            for (int64_t p = ext_ptr[g]; p < ext_ptr[g + 1]; ++p) acc = fma(-ext_val[p], x[ext_dep[p]], acc);
-        xs[loc] = acc;
-    }
+#pragma unroll 4
+    for (int loc = tid; loc < nr; loc += kPkThreads) xs[loc] = w[r0 + loc];
     __syncthreads();     // xs ready, barriers initialised
     for (int c = 0; c < nc; ++c) {
         const int b = c % kPkRing;
         pk_wait(bars + b, (uint32_t)((c / kPkRing) & 1));
-        const unsigned char* chunk = ring + b * kPkChunk;
-        const uint16_t* dir = reinterpret_cast<const uint16_t*>(chunk);
-        const int nseg = dir[0];
-        const uint16_t* seg_end = dir + 2;
-        const uint16_t* rec_off = seg_end + nseg;
-        int sb = 0;
-        for (int g = 0; g < nseg; ++g) {
-            const int se = seg_end[g];
-            for (int sl = sb + warp; sl < se; sl += NW) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
-            __syncthreads();
-            sb = se;
-        }
-        // every thread is past its last read of this ring buffer: refill it
+        pk_chunk<kPkThreads / 32, false>(ring + b * kPkChunk, lane, warp, xs);
+        // every thread is past its last read of this ring buffer (a segment ends with a barrier): refill it
         if (tid == 0 && c + kPkRing < nc) pk_fetch(ring + b * kPkChunk, src + (int64_t)(c + kPkRing) * kPkChunk, bars + b);
     }
+#pragma unroll 4
     for (int loc = tid; loc < nr; loc += kPkThreads) {
-        const int32_t u = prow_u[r0 + loc];
         const double r = xs[loc];
+        x[prow_u[r0 + loc]] = r;
+        if (out_scatter) out_scatter[prow_out[r0 + loc]] = r;
+    }
+}
+
+// Tiny subtrees (tens of thousands of 2-8 row chains hanging off the spine of the elimination tree):
+// one WARP per subtree.  Its whole packed description is one small blob (same format as a chunk),
+// copied to the warp's slice of shared memory with coalesced 16-byte loads; the levels then run
+// out of shared memory with __syncwarp: two global round trips per subtree instead of four per level.
+static constexpr int kPkWarpBlob = 2048;      // bytes; bigger subtrees go to tri_packed_kernel
+static constexpr int kPkWarpRows = 32;
+static constexpr int kPkWarpThreads = 256;
+
+__global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t count, const int64_t* __restrict__ blob_off,
+        const int64_t* __restrict__ row_off, const uint4* __restrict__ blobs, const int32_t* __restrict__ prow_u,
+        const int32_t* __restrict__ prow_out, const double* __restrict__ w, double* x, double* out_scatter,
+        const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    __shared__ __align__(16) unsigned char slices[kPkWarpThreads / 32][kPkWarpBlob];
+    __shared__ double xs_all[kPkWarpThreads / 32][kPkWarpRows];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * (kPkWarpThreads / 32) + warp;
+    if (t >= count) return;
+    const int64_t b0 = blob_off[t];
+    const int nb = (int)(blob_off[t + 1] - b0);          // 16-byte units
+    const int64_t r0 = row_off[t];
+    const int nr = (int)(row_off[t + 1] - r0);
+    uint4* slice = reinterpret_cast<uint4*>(slices[warp]);
+    double* xs = xs_all[warp];
+    for (int i = lane; i < nb; i += 32) slice[i] = blobs[b0 + i];
+    int32_t u = -1, po = -1;
+    if (lane < nr) {
+        xs[lane] = w[r0 + lane];
+        u = prow_u[r0 + lane];
+        if (out_scatter) po = prow_out[r0 + lane];
+    }
+    __syncwarp();
+    pk_chunk<1, true>(slices[warp], lane, 0, xs);
+    if (lane < nr) {
+        const double r = xs[lane];
         x[u] = r;
-        if (out_scatter) out_scatter[out_perm[u]] = r;
+        if (out_scatter) out_scatter[po] = r;
     }
 }
 
@@ -352,37 +346,41 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
     }
 }
 
-// the CTA-per-subtree kernel on `st`, the warp-per-subtree kernel concurrently on `side` (fork/join by events)
+// gather/external fold, then the packed CTA-per-subtree kernel on `st` and the warp-per-subtree kernel
+// concurrently on `side` (fork/join by events); the generic kernel only for subtrees that cannot be packed
 static int launch_subtrees(const TriSweep& S, const double* rhs, const int32_t* gather, double* x, double* out_scatter,
                            const int32_t* out_perm, const int* done, cudaStream_t st, const SweepStreams& ss) {
     int launches = 0;
-    const bool both = (S.n_sub_cta > 0 || S.n_sub_pack > 0) && S.n_sub_warp > 0;
+    if (S.pk_rows > 0) {
+        pk_gather_kernel<<<(unsigned)((S.pk_rows + 255) / 256), 256, 0, st>>>(S.pk_rows, S.pk_prow_src.p,
+            S.pk_has_ext ? S.pk_ext_ptr.p : nullptr, S.pk_ext_dep.p, S.pk_ext_val.p, rhs, x, S.pk_w.p, done);
+        ++launches;
+    }
+    const bool fork = S.n_sub_warp > 0 && (S.n_sub_pack > 0 || S.n_sub_cta > 0);
     cudaStream_t wst = st;
-    if (both) {
+    if (fork) {
         CUADMM_CUDA(cudaEventRecord(ss.fork, st));
         CUADMM_CUDA(cudaStreamWaitEvent(ss.side, ss.fork, 0));
         wst = ss.side;
     }
-    if (S.n_sub_warp > 0) {
-        const int wpb = kTriThreads / 32;
-        tri_subtree_warp_kernel<<<(unsigned)((S.n_sub_warp + wpb - 1) / wpb), kTriThreads, 0, wst>>>(S.n_sub_cta, S.n_sub_warp,
-            S.sub_off.p, S.sub_lvl_ptr.p, S.dep_loc.p, S.row_loc.p, S.slot_rows.p, S.slot_info.p, S.ptr.p, S.dep.p, S.val.p,
-            S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
-        ++launches;
-    }
     if (S.n_sub_pack > 0) {
         tri_packed_kernel<<<(unsigned)S.n_sub_pack, kPkThreads, S.pk_smem, st>>>(S.pk_chunk_off.p, S.pk_row_off.p, S.pk_stream.p,
-            S.pk_prow_u.p, S.pk_has_ext ? S.pk_ext_ptr.p : nullptr, S.pk_ext_dep.p, S.pk_ext_val.p, rhs, gather, x, out_scatter,
-            out_perm, done);
+            S.pk_prow_u.p, S.pk_prow_out.p, S.pk_w.p, x, out_scatter, done);
+        ++launches;
+    }
+    if (S.n_sub_warp > 0) {
+        const int wpb = kPkWarpThreads / 32;
+        tri_packed_warp_kernel<<<(unsigned)((S.n_sub_warp + wpb - 1) / wpb), kPkWarpThreads, 0, wst>>>(S.n_sub_warp,
+            S.pk_blob_off.p, S.pk_row_off.p + S.n_sub_pack, reinterpret_cast<const uint4*>(S.pk_blobs.p), S.pk_prow_u.p,
+            S.pk_prow_out.p, S.pk_w.p, x, out_scatter, done);
         ++launches;
     }
     if (S.n_sub_cta > 0) {
-        tri_subtree_kernel<<<(unsigned)S.n_sub_cta, kTriThreads, S.sub_smem, st>>>(S.sub_off.p, S.sub_lvl_ptr.p, S.dep_loc.p,
-            S.row_loc.p, S.slot_rows.p, S.slot_info.p, S.ptr.p, S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, out_scatter,
-            out_perm, done);
+        tri_subtree_kernel<<<(unsigned)S.n_sub_cta, kTriThreads, 0, st>>>(S.sub_off.p, S.sub_lvl_ptr.p, S.slot_rows.p, S.slot_info.p,
+            S.ptr.p, S.dep.p, S.val.p, S.inv_diag.p, rhs, gather, x, out_scatter, out_perm, done);
         ++launches;
     }
-    if (both) {
+    if (fork) {
         CUADMM_CUDA(cudaEventRecord(ss.join, ss.side));
         CUADMM_CUDA(cudaStreamWaitEvent(st, ss.join, 0));
     }
@@ -420,6 +418,8 @@ struct HostSweep {
     std::vector<int32_t> sub;       // per unknown id: subtree id, or -1 = top part
     int64_t n_sub = 0;
     bool subtrees_first = true;     // forward: subtrees then top; backward: top then subtrees
+    const std::vector<int32_t>* gather = nullptr;     // rhs is read at gather[u] (null: at u)
+    const std::vector<int32_t>* out_perm = nullptr;   // results are also scattered to out[out_perm[u]] (null: no scatter)
 };
 
 // slots for a list of unknowns that all belong to one level
@@ -444,21 +444,34 @@ static int64_t emit_level_slots(const HostSweep& H, std::vector<int32_t>& rows, 
     return cnt;
 }
 
-// host side of tri_packed_kernel: chunk streams, row lists and the external (out-of-subtree) entries
+// Host side of the packed subtree kernels.  Decides per subtree: 2 = CTA-packed (chunk stream),
+// 1 = warp-packed (one small blob), 0 = not packable (generic kernel); builds the streams, the unified
+// row lists (CTA-packed subtrees first, then warp-packed) and the external (out-of-subtree) entries.
 static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std::vector<int32_t>>& members,
-                          const std::vector<int32_t>& level, const std::vector<int32_t>& depth, const std::vector<int>& kind) {
-    struct Packed { std::vector<unsigned char> bytes; int32_t t; };
-    std::vector<Packed> packs;
-    std::vector<int32_t> loc(H.n, -1);
-    for (int64_t t = 0; t < H.n_sub; ++t) {
-        if (kind[t] != 2) continue;
+                          const std::vector<int32_t>& level, const std::vector<int32_t>& depth, std::vector<int>& kind) {
+    struct Packed { std::vector<unsigned char> bytes; int32_t t; size_t last_used; };
+    std::vector<Packed> packs, blobs;
+    std::vector<int32_t> loc(H.n, -1), loc_cnt(H.n, 0);
+    bool use_packed = true;
+    if (const char* e = getenv("CUADMM_SWEEP_PACKED")) use_packed = atoi(e) != 0;
+    kind.assign(H.n_sub, 0);
+    for (int64_t t = 0; t < H.n_sub && use_packed; ++t) {
         const std::vector<int32_t>& rows = members[t];
-        for (size_t q = 0; q < rows.size(); ++q) loc[rows[q]] = (int32_t)q;
+        if ((int64_t)rows.size() > kPkMaxRows) continue;
+        int32_t longest = 0;
+        for (size_t q = 0; q < rows.size(); ++q) {
+            const int32_t u = rows[q];
+            loc[u] = (int32_t)q;
+            int32_t cnt = 0;
+            for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) cnt += (H.sub[H.dep[p]] == H.sub[u]) ? 1 : 0;
+            loc_cnt[u] = cnt;
+            longest = std::max(longest, cnt);
+        }
+        if (longest > kPkMaxRowEntries) continue;
         std::vector<std::vector<int32_t>> by_level(depth[t]);
         for (int32_t u : rows) by_level[level[u]].push_back(u);
-        Packed P; P.t = (int32_t)t;
-        // open chunk state
-        std::vector<uint16_t> seg_end, rec_rel;      // rec_rel: record offsets (bytes) inside the records area
+        Packed P; P.t = (int32_t)t; P.last_used = 0;
+        std::vector<uint16_t> seg_end, rec_rel;      // open chunk; rec_rel: record offsets (bytes) inside the records area
         std::vector<unsigned char> recs;
         auto dir_bytes = [](size_t nseg, size_t nslots) { return (4 + 2 * nseg + 2 * nslots + 7) / 8 * 8; };
         auto close_chunk = [&]() {
@@ -473,17 +486,17 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
             CUADMM_REQUIRE(db + recs.size() <= (size_t)kPkChunk, "internal: packed chunk overflow");
             std::copy(recs.begin(), recs.end(), chunk.begin() + db);
             P.bytes.insert(P.bytes.end(), chunk.begin(), chunk.end());
+            P.last_used = db + recs.size();
             seg_end.clear(); rec_rel.clear(); recs.clear();
         };
         auto add_record = [&](const std::vector<unsigned char>& rec, bool new_level) {
-            size_t nseg = seg_end.size() + 1 + ((new_level && !rec_rel.empty()) ? 1 : 0);
+            const size_t nseg = seg_end.size() + 1 + ((new_level && !rec_rel.empty()) ? 1 : 0);
             if (dir_bytes(nseg, rec_rel.size() + 1) + recs.size() + rec.size() > (size_t)kPkChunk) close_chunk();
             if (new_level && !rec_rel.empty()) seg_end.push_back((uint16_t)rec_rel.size());
             rec_rel.push_back((uint16_t)recs.size());
             recs.insert(recs.end(), rec.begin(), rec.end());
         };
         auto make_record = [&](const int32_t* us, int nrows, bool is_long) {
-            int ne = 0;
             std::vector<int32_t> uloc(8, -1);
             std::vector<uint16_t> start(8, 0), len(8, 0);
             std::vector<double> invd(8, 0.0), val;
@@ -495,27 +508,23 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
                     if (H.sub[H.dep[p]] == H.sub[u]) { val.push_back(H.val[p]); idx.push_back((uint16_t)loc[H.dep[p]]); }
                 len[r] = (uint16_t)(val.size() - start[r]);
             }
-            ne = (int)val.size();
-            std::vector<unsigned char> rec(kPkRecHeader + 8 * (size_t)ne + (2 * (size_t)ne + 7) / 8 * 8, 0);
+            const size_t ne = val.size();
+            std::vector<unsigned char> rec(kPkRecHeader + 8 * ne + (2 * ne + 7) / 8 * 8, 0);
             int32_t* hdr = reinterpret_cast<int32_t*>(rec.data());
-            hdr[0] = ne; hdr[1] = is_long ? 1 : 0;
+            hdr[0] = (int32_t)ne; hdr[1] = is_long ? 1 : 0;
             std::copy(uloc.begin(), uloc.end(), hdr + 2);
             std::copy(start.begin(), start.end(), reinterpret_cast<uint16_t*>(rec.data() + 40));
             std::copy(len.begin(), len.end(), reinterpret_cast<uint16_t*>(rec.data() + 56));
             std::copy(invd.begin(), invd.end(), reinterpret_cast<double*>(rec.data() + 72));
             if (ne) {
                 std::copy(val.begin(), val.end(), reinterpret_cast<double*>(rec.data() + kPkRecHeader));
-                std::copy(idx.begin(), idx.end(), reinterpret_cast<uint16_t*>(rec.data() + kPkRecHeader + 8 * (size_t)ne));
+                std::copy(idx.begin(), idx.end(), reinterpret_cast<uint16_t*>(rec.data() + kPkRecHeader + 8 * ne));
             }
             return rec;
         };
         for (int l = 0; l < depth[t]; ++l) {
             std::vector<int32_t> longs, shorts;
-            for (int32_t u : by_level[l]) {
-                int cnt = 0;
-                for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) cnt += (H.sub[H.dep[p]] == H.sub[u]) ? 1 : 0;
-                (cnt > kLongRowNnz ? longs : shorts).push_back(u);
-            }
+            for (int32_t u : by_level[l]) (loc_cnt[u] > kLongRowNnz ? longs : shorts).push_back(u);
             bool first = true;
             for (int32_t u : longs) { add_record(make_record(&u, 1, true), first); first = false; }
             for (size_t q = 0; q < shorts.size(); q += 8) {
@@ -524,42 +533,65 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
             }
         }
         close_chunk();
-        packs.push_back(std::move(P));
+        if ((int64_t)rows.size() <= kPkWarpRows && P.bytes.size() == (size_t)kPkChunk && P.last_used <= (size_t)kPkWarpBlob) {
+            P.bytes.resize((P.last_used + 15) / 16 * 16);
+            kind[t] = 1;
+            blobs.push_back(std::move(P));
+        } else {
+            kind[t] = 2;
+            packs.push_back(std::move(P));
+        }
     }
     S.n_sub_pack = (int64_t)packs.size();
-    S.pk_smem = 0;
-    if (packs.empty()) return;
+    S.n_sub_warp = (int64_t)blobs.size();
+    S.pk_smem = 0; S.pk_rows = 0;
+    if (packs.empty() && blobs.empty()) return;
+    // biggest first: CTAs are dispatched in index order
     std::stable_sort(packs.begin(), packs.end(), [](const Packed& a, const Packed& b) { return a.bytes.size() > b.bytes.size(); });
-    std::vector<int64_t> chunk_off(1, 0), row_off(1, 0), ext_ptr(1, 0);
-    std::vector<int32_t> prow_u, ext_dep;
+    std::stable_sort(blobs.begin(), blobs.end(), [&](const Packed& a, const Packed& b) { return depth[a.t] > depth[b.t]; });
+    std::vector<int64_t> chunk_off(1, 0), blob_off(1, 0), row_off(1, 0), ext_ptr(1, 0);
+    std::vector<int32_t> prow_u, prow_src, prow_out, ext_dep;
     std::vector<double> ext_val;
-    std::vector<unsigned char> stream;
-    size_t total = 0;
-    for (const Packed& P : packs) total += P.bytes.size();
-    stream.reserve(total);
+    std::vector<unsigned char> stream, blob_bytes;
     int64_t max_rows = 0;
-    for (const Packed& P : packs) {
-        stream.insert(stream.end(), P.bytes.begin(), P.bytes.end());
-        chunk_off.push_back((int64_t)(stream.size() / kPkChunk));
-        for (int32_t u : members[P.t]) {
+    auto add_rows = [&](int32_t t) {
+        for (int32_t u : members[t]) {
             prow_u.push_back(u);
+            prow_src.push_back(H.gather ? (*H.gather)[u] : u);
+            prow_out.push_back(H.out_perm ? (*H.out_perm)[u] : 0);
             for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
                 if (H.sub[H.dep[p]] != H.sub[u]) { ext_dep.push_back(H.dep[p]); ext_val.push_back(H.val[p]); }
             ext_ptr.push_back((int64_t)ext_dep.size());
         }
         row_off.push_back((int64_t)prow_u.size());
+    };
+    for (const Packed& P : packs) {
+        stream.insert(stream.end(), P.bytes.begin(), P.bytes.end());
+        chunk_off.push_back((int64_t)(stream.size() / kPkChunk));
+        add_rows(P.t);
         max_rows = std::max<int64_t>(max_rows, (int64_t)members[P.t].size());
     }
+    for (const Packed& P : blobs) {
+        blob_bytes.insert(blob_bytes.end(), P.bytes.begin(), P.bytes.end());
+        blob_off.push_back((int64_t)(blob_bytes.size() / 16));
+        add_rows(P.t);
+    }
+    S.pk_rows = (int64_t)prow_u.size();
     S.pk_has_ext = !ext_dep.empty();
     if (ext_dep.empty()) { ext_dep.push_back(0); ext_val.push_back(0.0); }
-    S.pk_stream.upload(stream); S.pk_chunk_off.upload(chunk_off); S.pk_row_off.upload(row_off);
-    S.pk_prow_u.upload(prow_u); S.pk_ext_ptr.upload(ext_ptr); S.pk_ext_dep.upload(ext_dep); S.pk_ext_val.upload(ext_val);
+    if (stream.empty()) stream.assign(16, 0);
+    if (blob_bytes.empty()) blob_bytes.assign(16, 0);
+    S.pk_stream.upload(stream); S.pk_chunk_off.upload(chunk_off); S.pk_blobs.upload(blob_bytes); S.pk_blob_off.upload(blob_off);
+    S.pk_row_off.upload(row_off); S.pk_prow_u.upload(prow_u); S.pk_prow_src.upload(prow_src); S.pk_prow_out.upload(prow_out);
+    S.pk_ext_ptr.upload(ext_ptr); S.pk_ext_dep.upload(ext_dep); S.pk_ext_val.upload(ext_val);
+    S.pk_w.alloc(S.pk_rows);
     S.pk_smem = (size_t)kPkRing * kPkChunk + 64 + sizeof(double) * (size_t)max_rows;
     CUADMM_CUDA(cudaFuncSetAttribute((const void*)tri_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.pk_smem));
     if (getenv("CUADMM_YSOLVE_VERBOSE"))
-        fprintf(stderr, "[ysolve] packed: %lld subtrees, %lld rows, %lld chunks (largest %lld), %lld external entries, smem %zu\n",
-                (long long)packs.size(), (long long)prow_u.size(), (long long)chunk_off.back(),
-                (long long)(packs[0].bytes.size() / kPkChunk), (long long)ext_ptr.back(), S.pk_smem);
+        fprintf(stderr, "[ysolve] %s packed: %zu CTA subtrees in %lld chunks (largest %zu), %zu warp subtrees in %zu bytes, "
+                "%lld rows, %lld external entries, smem %zu\n", H.subtrees_first ? "fwd" : "bwd", packs.size(),
+                (long long)chunk_off.back(), packs.empty() ? (size_t)0 : packs[0].bytes.size() / kPkChunk, blobs.size(),
+                blob_bytes.size(), (long long)S.pk_rows, (long long)ext_ptr.back(), S.pk_smem);
 }
 
 static void upload_sweep(const HostSweep& H, TriSweep& S) {
@@ -578,43 +610,20 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
         level[u] = l;
     }
     std::vector<int32_t> slot_rows, slot_info;
-    // ---- subtree part: slots grouped by (subtree, level); deepest subtrees first
+    // ---- subtree part
     std::vector<std::vector<int32_t>> members(H.n_sub);
     std::vector<int32_t> depth(H.n_sub, 0);
     for (int32_t u : H.order) if (H.sub[u] >= 0) {
         members[H.sub[u]].push_back(u);
         depth[H.sub[u]] = std::max(depth[H.sub[u]], level[u] + 1);
     }
-    std::vector<int32_t> sub_order(H.n_sub);
-    std::iota(sub_order.begin(), sub_order.end(), 0);
-    // three groups: packed (TMA-streamed CTA per subtree), generic CTA per subtree (fallback), warp per subtree
-    bool use_packed = true;
-    if (const char* e = getenv("CUADMM_SWEEP_PACKED")) use_packed = atoi(e) != 0;
-    std::vector<int32_t> loc_cnt(H.n, 0);
-    for (int32_t u : H.order) if (H.sub[u] >= 0)
-        for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) loc_cnt[u] += (H.sub[H.dep[p]] == H.sub[u]) ? 1 : 0;
-    std::vector<int> kind(H.n_sub, 0);          // 0 generic, 1 warp, 2 packed
-    for (int64_t t = 0; t < H.n_sub; ++t) {
-        const int64_t rows = (int64_t)members[t].size();
-        if (rows <= kWarpSubRows) { kind[t] = 1; continue; }
-        int32_t longest = 0;
-        for (int32_t u : members[t]) longest = std::max(longest, loc_cnt[u]);
-        if (use_packed && rows <= kPkMaxRows && longest <= kPkMaxRowEntries) kind[t] = 2;
-    }
-    auto small = [&](int32_t t) { return kind[t] == 1; };
-    {
-        std::vector<int32_t> keep;
-        for (int32_t t : sub_order) if (kind[t] != 2) keep.push_back(t);
-        sub_order.swap(keep);
-    }
-    std::stable_sort(sub_order.begin(), sub_order.end(), [&](int32_t a, int32_t b) {
-        if (small(a) != small(b)) return small(b);
-        return depth[a] > depth[b];
-    });
-    S.n_sub_warp = 0;
-    for (int32_t t : sub_order) S.n_sub_warp += small(t) ? 1 : 0;
-    S.n_sub_cta = (int64_t)sub_order.size() - S.n_sub_warp;
+    std::vector<int> kind;
     pack_subtrees(H, S, members, level, depth, kind);
+    // whatever could not be packed: generic CTA-per-subtree kernel, slots grouped by (subtree, level), deepest first
+    std::vector<int32_t> sub_order;
+    for (int64_t t = 0; t < H.n_sub; ++t) if (kind[t] == 0) sub_order.push_back((int32_t)t);
+    std::stable_sort(sub_order.begin(), sub_order.end(), [&](int32_t a, int32_t b) { return depth[a] > depth[b]; });
+    S.n_sub_cta = (int64_t)sub_order.size();
     std::vector<int64_t> sub_off(1, 0), sub_lvl_ptr;
     int max_sub_depth = 0;
     for (int32_t t : sub_order) {
@@ -626,31 +635,11 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
         }
         sub_lvl_ptr.push_back((int64_t)slot_info.size());
         sub_off.push_back((int64_t)sub_lvl_ptr.size());
-        max_sub_depth = std::max(max_sub_depth, depth[t]);
     }
+    for (int64_t t = 0; t < H.n_sub; ++t) max_sub_depth = std::max(max_sub_depth, depth[t]);
     S.n_sub = H.n_sub;
     S.sub_depth = max_sub_depth;
-    // shared-memory residency: local index of every subtree unknown, and per entry the local index of
-    // its dependency when that lives in the same subtree (-1: read the global vector)
-    std::vector<int32_t> row_loc(H.n, -1), dep_loc(std::max<size_t>(H.dep.size(), 1), -1);
-    int64_t max_rows = 0;
-    for (int64_t t = 0; t < H.n_sub; ++t) {
-        if (kind[t] == 2) continue;
-        for (size_t q = 0; q < members[t].size(); ++q) row_loc[members[t][q]] = (int32_t)q;
-        if (!small((int32_t)t)) max_rows = std::max<int64_t>(max_rows, (int64_t)members[t].size());
-    }
-    for (int32_t u : H.order) if (H.sub[u] >= 0 && kind[H.sub[u]] != 2)
-        for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) if (H.sub[H.dep[p]] == H.sub[u]) dep_loc[p] = row_loc[H.dep[p]];
-    S.row_loc.upload(row_loc); S.dep_loc.upload(dep_loc);
     if (getenv("CUADMM_YSOLVE_VERBOSE")) {
-        int64_t rows = 0, lv = 0;
-        for (int64_t t = 0; t < H.n_sub; ++t) { rows += (int64_t)members[t].size(); lv += depth[t]; }
-        fprintf(stderr, "[ysolve] %s sweep: %lld subtrees, %lld rows, %lld slots, max rows %lld, sum depth %lld; deepest:",
-                H.subtrees_first ? "fwd" : "bwd", (long long)H.n_sub, (long long)rows, (long long)slot_info.size(),
-                (long long)max_rows, (long long)lv);
-        for (size_t q = 0; q < std::min<size_t>(8, sub_order.size()); ++q)
-            fprintf(stderr, " %d/%zu", depth[sub_order[q]], members[sub_order[q]].size());
-        fprintf(stderr, "\n");
         const int64_t edges[] = {8, 32, 128, 256, 512, 1024, 2048, 4096, 1 << 30};
         for (int b = 0; b < 9; ++b) {
             int64_t cnt = 0, r = 0, dsum = 0; int dmax = 0;
@@ -658,13 +647,10 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
                 const int64_t sz = (int64_t)members[t].size();
                 if (sz <= edges[b] && (b == 0 || sz > edges[b - 1])) { ++cnt; r += sz; dsum += depth[t]; dmax = std::max(dmax, depth[t]); }
             }
-            fprintf(stderr, "[ysolve]   rows<=%lld: %lld subtrees, %lld rows, sum depth %lld, max depth %d\n",
-                    (long long)edges[b], (long long)cnt, (long long)r, (long long)dsum, dmax);
+            if (cnt) fprintf(stderr, "[ysolve]   rows<=%lld: %lld subtrees, %lld rows, sum depth %lld, max depth %d\n",
+                             (long long)edges[b], (long long)cnt, (long long)r, (long long)dsum, dmax);
         }
     }
-    S.sub_smem = sizeof(double) * (size_t)max_rows;
-    if (S.sub_smem > 48 * 1024)
-        CUADMM_CUDA(cudaFuncSetAttribute((const void*)tri_subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.sub_smem));
     // ---- top part: global levels, wide levels one launch each, narrow runs in one CTA
     int maxlev = -1;
     for (int32_t u : H.order) if (H.sub[u] < 0) maxlev = std::max(maxlev, (int)level[u]);
@@ -824,6 +810,7 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         H.order.resize(m);
         std::iota(H.order.begin(), H.order.end(), 0);
         H.sub = sub; H.n_sub = n_sub; H.subtrees_first = true;
+        H.gather = &Y->h_perm;
         upload_sweep(H, Y->fwd);
     }
     // ---- backward sweep: columns of L as rows of L^T, lead unknowns only
@@ -846,6 +833,7 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         H.sub = sub;
         for (int64_t i = n_lead; i < m; ++i) H.sub[i] = -2;
         H.n_sub = n_sub; H.subtrees_first = false;
+        H.out_perm = &Y->h_perm;
         upload_sweep(H, Y->bwd);
     }
     Y->z.alloc(std::max<int64_t>(m, 1));
@@ -859,7 +847,8 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         Y->tail_tmp.alloc(n_tail);
     }
     Y->launches_per_solve = (int)(Y->fwd.phases.size() + Y->bwd.phases.size()) + (n_tail > 0 ? 2 : 0) +
-                            (Y->fwd.n_sub_cta > 0 ? 2 : 0) + (Y->fwd.n_sub_warp > 0 ? 2 : 0) + (Y->fwd.n_sub_pack > 0 ? 2 : 0);
+                            (Y->fwd.n_sub_cta > 0 ? 2 : 0) + (Y->fwd.n_sub_warp > 0 ? 2 : 0) + (Y->fwd.n_sub_pack > 0 ? 2 : 0) +
+                            (Y->fwd.pk_rows > 0 ? 2 : 0);
     CUADMM_CUDA(cudaStreamCreateWithFlags(&Y->streams.side, cudaStreamNonBlocking));
     CUADMM_CUDA(cudaEventCreateWithFlags(&Y->streams.fork, cudaEventDisableTiming));
     CUADMM_CUDA(cudaEventCreateWithFlags(&Y->streams.join, cudaEventDisableTiming));

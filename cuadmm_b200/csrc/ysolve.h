@@ -26,15 +26,14 @@ struct TriSweep {
     int levels = 0;               // levels of the top part
     // subtree part: CTA t walks levels [sub_off[t], sub_off[t+1]-1) of sub_lvl_ptr (slot offsets)
     DevBuf<int64_t> sub_off, sub_lvl_ptr;
-    DevBuf<int32_t> dep_loc, row_loc;   // shared-memory indices (see ysolve.cu)
-    size_t sub_smem = 0;
-    int64_t n_sub = 0, n_sub_cta = 0, n_sub_warp = 0;   // CTA-per-subtree group first, warp-per-subtree group after
-    // packed subtrees (TMA-streamed, see tri_packed_kernel)
-    int64_t n_sub_pack = 0;
-    DevBuf<unsigned char> pk_stream;
-    DevBuf<int64_t> pk_chunk_off, pk_row_off, pk_ext_ptr;
-    DevBuf<int32_t> pk_prow_u, pk_ext_dep;
-    DevBuf<double> pk_ext_val;
+    int64_t n_sub = 0;            // all subtrees = n_sub_pack + n_sub_warp + n_sub_cta
+    int64_t n_sub_cta = 0;        // generic CTA-per-subtree kernel (not packable), indexed by sub_off
+    // packed subtrees (see tri_packed_kernel / tri_packed_warp_kernel); rows of the CTA-packed ones first
+    int64_t n_sub_pack = 0, n_sub_warp = 0, pk_rows = 0;
+    DevBuf<unsigned char> pk_stream, pk_blobs;
+    DevBuf<int64_t> pk_chunk_off, pk_blob_off, pk_row_off, pk_ext_ptr;
+    DevBuf<int32_t> pk_prow_u, pk_prow_src, pk_prow_out, pk_ext_dep;
+    DevBuf<double> pk_ext_val, pk_w;
     size_t pk_smem = 0;
     bool pk_has_ext = false;
     int sub_depth = 0;
