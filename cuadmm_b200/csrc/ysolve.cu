@@ -157,18 +157,26 @@ __global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t*
 //
 // chunk:  u16 nseg, u16 nslots, u16 seg_end[nseg], u16 rec_off[nslots] (8-byte units), records...
 //         a segment = consecutive slots of one level; every segment ends with a barrier.
-// record: i32 ne, i32 is_long, i32 uloc[8], u16 start[8], u16 len[8], f64 inv_diag[8], f64 val[ne], u16 idx[ne]
+// record: i32 is_long, i32 ne, i32 slot[8], u16 voff[8] (8-byte units), u16 ioff[8] (2-byte units), u16 len[8],
+//         f64 inv_diag[8], f64 val[ne], u16 idx[ne]
 //         (8 short rows x 4 lanes, or one long row x 32 lanes; idx = shared-memory index of the dependency)
 // Dependencies OUTSIDE the subtree are final when the kernel starts; the prologue folds them into
 // the right-hand side:  xs[loc] = rhs[u] - sum_ext val * x[dep].
-static constexpr int kPkChunk = 8192;
-static constexpr int kPkRing = 5;
-static constexpr int kPkThreads = 512;
-static constexpr int kPkRecHeader = 8 + 32 + 16 + 16 + 64;
+static constexpr int kPkChunk = 16384;
+static constexpr int kPkRing = 4;
+static constexpr int kPkThreads = 1024;
+static constexpr int kPkRecHeader = 8 + 32 + 16 + 16 + 16 + 64;
 static constexpr int kPkMaxRowEntries = 768;
 static constexpr int kPkMaxRows = 23000;
+static constexpr int kPkChainMax = 384;        // unknowns in a collapsed chain (dense inverse kPkChainMax^2 / 2 entries)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ long long pk_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void pk_fetch(unsigned char* dst, const unsigned char* src, uint64_t* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(kPkChunk) : "memory");
@@ -185,24 +193,23 @@ __device__ __forceinline__ void pk_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ void pk_record(const unsigned char* rec, int lane, double* xs) {
-    const int32_t* hdr = reinterpret_cast<const int32_t*>(rec);
-    const int ne = hdr[0];
-    const bool is_long = hdr[1] != 0;
-    const int32_t* uloc = hdr + 2;
-    const uint16_t* start = reinterpret_cast<const uint16_t*>(rec + 40);
-    const uint16_t* len = start + 8;
-    const double* invd = reinterpret_cast<const double*>(rec + 72);
-    const double* val = invd + 8;
-    const uint16_t* idx = reinterpret_cast<const uint16_t*>(val + ne);
-    const int r = is_long ? 0 : (lane >> 2);
+    // round 1: everything in the header is addressable from the lane id alone (a long record
+    // replicates its single row into all 8 header positions)
+    const int r = lane >> 2;
+    const bool is_long = *reinterpret_cast<const int32_t*>(rec) != 0;
+    const int ul = reinterpret_cast<const int32_t*>(rec + 8)[r];
+    const int voff = reinterpret_cast<const uint16_t*>(rec + 40)[r];
+    const int ioff = reinterpret_cast<const uint16_t*>(rec + 56)[r];
+    const int ln = reinterpret_cast<const uint16_t*>(rec + 72)[r];
+    const double invd = reinterpret_cast<const double*>(rec + 88)[r];
     const int j = is_long ? lane : (lane & 3);
     const int step = is_long ? 32 : 4;
-    const int ul = uloc[r];
+    const double* val = reinterpret_cast<const double*>(rec) + voff;
+    const uint16_t* idx = reinterpret_cast<const uint16_t*>(rec) + ioff;
+    // round 2: values, indices, the slot's current content; round 3: the unknowns
+    const double cur = ul >= 0 ? xs[ul] : 0.0;
     double acc = 0.0;
-    if (ul >= 0) {
-        const int st = start[r], ln = len[r];
-        for (int k = j; k < ln; k += step) acc = fma(val[st + k], xs[idx[st + k]], acc);
-    }
+    for (int k = j; k < ln; k += step) acc = fma(val[k], xs[idx[k]], acc);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (is_long) {
@@ -210,7 +217,7 @@ __device__ __forceinline__ void pk_record(const unsigned char* rec, int lane, do
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
     }
-    if (ul >= 0 && j == 0) xs[ul] = (xs[ul] - acc) * invd[r];
+    if (ul >= 0 && j == 0) xs[ul] = (cur - acc) * invd;
 }
 
 // w[g] = rhs[src[g]] - sum over the row's dependencies OUTSIDE its subtree (all final by now) of
@@ -222,7 +229,8 @@ __global__ void __launch_bounds__(256) pk_gather_kernel(int64_t n_rows, const in
     if (done_flag && *done_flag) return;
     const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (g >= n_rows) return;
-    double acc = rhs[prow_src[g]];
+    const int32_t src = prow_src[g];
+    double acc = src >= 0 ? rhs[src] : 0.0;        // src < 0: a slot that starts from zero (see pack_subtrees)
     if (ext_ptr)
         for (int64_t p = ext_ptr[g]; p < ext_ptr[g + 1]; ++p) acc = fma(-ext_val[p], x[ext_dep[p]], acc);
     w[g] = acc;
@@ -247,8 +255,9 @@ __device__ __forceinline__ void pk_chunk(const unsigned char* chunk, int lane, i
 __global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* __restrict__ chunk_off,
         const int64_t* __restrict__ row_off, const unsigned char* __restrict__ stream, const int32_t* __restrict__ prow_u,
         const int32_t* __restrict__ prow_out, const double* __restrict__ w, double* x, double* out_scatter,
-        const int* __restrict__ done_flag) {
+        const int* __restrict__ done_flag, long long* __restrict__ timeline) {
     if (done_flag && *done_flag) return;
+    if (timeline && threadIdx.x == 0) timeline[4 * blockIdx.x + 0] = pk_globaltimer();
     extern __shared__ __align__(128) unsigned char pk_smem[];
     unsigned char* ring = pk_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(pk_smem + kPkRing * kPkChunk);
@@ -269,6 +278,7 @@ __global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* _
 #pragma unroll 4
     for (int loc = tid; loc < nr; loc += kPkThreads) xs[loc] = w[r0 + loc];
     __syncthreads();     // xs ready, barriers initialised
+    if (timeline && tid == 0) timeline[4 * blockIdx.x + 1] = pk_globaltimer();
     for (int c = 0; c < nc; ++c) {
         const int b = c % kPkRing;
         pk_wait(bars + b, (uint32_t)((c / kPkRing) & 1));
@@ -276,12 +286,16 @@ __global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* _
         // every thread is past its last read of this ring buffer (a segment ends with a barrier): refill it
         if (tid == 0 && c + kPkRing < nc) pk_fetch(ring + b * kPkChunk, src + (int64_t)(c + kPkRing) * kPkChunk, bars + b);
     }
+    if (timeline && tid == 0) timeline[4 * blockIdx.x + 2] = pk_globaltimer();
 #pragma unroll 4
     for (int loc = tid; loc < nr; loc += kPkThreads) {
+        const int32_t u = prow_u[r0 + loc];
+        if (u < 0) continue;                        // scratch slot, not an unknown
         const double r = xs[loc];
-        x[prow_u[r0 + loc]] = r;
+        x[u] = r;
         if (out_scatter) out_scatter[prow_out[r0 + loc]] = r;
     }
+    if (timeline && tid == 0) timeline[4 * blockIdx.x + 3] = pk_globaltimer();
 }
 
 // Tiny subtrees (tens of thousands of 2-8 row chains hanging off the spine of the elimination tree):
@@ -317,7 +331,7 @@ __global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t
     }
     __syncwarp();
     pk_chunk<1, true>(slices[warp], lane, 0, xs);
-    if (lane < nr) {
+    if (lane < nr && u >= 0) {
         const double r = xs[lane];
         x[u] = r;
         if (out_scatter) out_scatter[po] = r;
@@ -365,7 +379,7 @@ static int launch_subtrees(const TriSweep& S, const double* rhs, const int32_t* 
     }
     if (S.n_sub_pack > 0) {
         tri_packed_kernel<<<(unsigned)S.n_sub_pack, kPkThreads, S.pk_smem, st>>>(S.pk_chunk_off.p, S.pk_row_off.p, S.pk_stream.p,
-            S.pk_prow_u.p, S.pk_prow_out.p, S.pk_w.p, x, out_scatter, done);
+            S.pk_prow_u.p, S.pk_prow_out.p, S.pk_w.p, x, out_scatter, done, S.pk_timeline.n ? S.pk_timeline.p : nullptr);
         ++launches;
     }
     if (S.n_sub_warp > 0) {
@@ -446,31 +460,146 @@ static int64_t emit_level_slots(const HostSweep& H, std::vector<int32_t>& rows, 
 
 // Host side of the packed subtree kernels.  Decides per subtree: 2 = CTA-packed (chunk stream),
 // 1 = warp-packed (one small blob), 0 = not packable (generic kernel); builds the streams, the unified
-// row lists (CTA-packed subtrees first, then warp-packed) and the external (out-of-subtree) entries.
+// slot lists (CTA-packed subtrees first, then warp-packed) and the external (out-of-subtree) entries.
+//
+// Chain collapse.  The top of a subtree of the elimination tree is typically a chain: ~130 levels of
+// ONE dense-ish row each, i.e. a small dense triangular system L_CC solved one row per barrier.  For
+// such a set C (at most kPkChainMax unknowns, chosen by level so that it is closed the right way) the
+// host inverts L_CC once, M = L_CC^-1, and the sweep computes x_C = M t_C as ONE level of independent
+// dense rows, t_C = b_C - (contributions from outside C).  Two flavours, whichever the sweep needs:
+//   final set   (forward sweep):  C = {level >= l0}; nothing outside C depends on C;
+//                                 levels: R rows (unchanged), t_C = b_C - L_CR x_R, x_C = M t_C;
+//   initial set (backward sweep): C = {height >= h0}; C depends on nothing outside C (in the subtree);
+//                                 levels: x_C = M t_C, then the R rows with levels counted inside R.
+// t_C lives in extra scratch slots behind the subtree's unknowns so that x_C = M t_C has no in-place hazard.
+struct PkRow {                       // one row of one level: slot = (slot - sum val * xs[idx]) * invd
+    int32_t slot; double invd;
+    std::vector<uint16_t> idx; std::vector<double> val;
+};
+
 static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std::vector<int32_t>>& members,
                           const std::vector<int32_t>& level, const std::vector<int32_t>& depth, std::vector<int>& kind) {
-    struct Packed { std::vector<unsigned char> bytes; int32_t t; size_t last_used; };
+    struct Packed {
+        std::vector<unsigned char> bytes; int32_t t; size_t last_used; int levels;
+        std::vector<int32_t> slot_u, slot_src;      // per slot: unknown to write (-1 none), unknown to start from (-1: zero)
+    };
     std::vector<Packed> packs, blobs;
-    std::vector<int32_t> loc(H.n, -1), loc_cnt(H.n, 0);
+    std::vector<int32_t> loc(H.n, -1), cidx(H.n, -1), height(H.n, 0), lvl_r(H.n, 0);
     bool use_packed = true;
     if (const char* e = getenv("CUADMM_SWEEP_PACKED")) use_packed = atoi(e) != 0;
+    int chain_max = kPkChainMax, chain_gain = 6;
+    if (const char* e = getenv("CUADMM_SWEEP_CHAIN_MAX")) chain_max = std::min(atoi(e), kPkMaxRowEntries);
+    const bool verbose = getenv("CUADMM_YSOLVE_VERBOSE") != nullptr;
+    int64_t n_collapsed = 0, levels_before = 0, levels_after = 0, chain_entries = 0;
     kind.assign(H.n_sub, 0);
+    auto same = [&](int32_t u, int64_t p) { return H.sub[H.dep[p]] == H.sub[u]; };
     for (int64_t t = 0; t < H.n_sub && use_packed; ++t) {
-        const std::vector<int32_t>& rows = members[t];
-        if ((int64_t)rows.size() > kPkMaxRows) continue;
+        const std::vector<int32_t>& rows = members[t];       // in solve order
+        const int32_t nr0 = (int32_t)rows.size();
+        if (nr0 + chain_max > kPkMaxRows) continue;
         int32_t longest = 0;
-        for (size_t q = 0; q < rows.size(); ++q) {
+        for (int32_t q = 0; q < nr0; ++q) {
             const int32_t u = rows[q];
-            loc[u] = (int32_t)q;
+            loc[u] = q;
             int32_t cnt = 0;
-            for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) cnt += (H.sub[H.dep[p]] == H.sub[u]) ? 1 : 0;
-            loc_cnt[u] = cnt;
+            for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) cnt += same(u, p) ? 1 : 0;
             longest = std::max(longest, cnt);
         }
         if (longest > kPkMaxRowEntries) continue;
-        std::vector<std::vector<int32_t>> by_level(depth[t]);
-        for (int32_t u : rows) by_level[level[u]].push_back(u);
-        Packed P; P.t = (int32_t)t; P.last_used = 0;
+        // ---- chain collapse: pick C
+        std::vector<int32_t> C;
+        int new_depth = depth[t], k0 = 0;
+        if (chain_max > 0 && depth[t] > chain_gain + 2 && nr0 > kPkWarpRows) {
+            const bool initial = !H.subtrees_first;             // backward sweep
+            std::vector<int32_t> key(nr0);
+            if (initial) {
+                for (int32_t u : rows) height[u] = 0;
+                for (int32_t q = nr0 - 1; q >= 0; --q) {        // reverse solve order: dependents first
+                    const int32_t u = rows[q];
+                    for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
+                        if (same(u, p)) height[H.dep[p]] = std::max(height[H.dep[p]], height[u] + 1);
+                }
+                for (int32_t q = 0; q < nr0; ++q) key[q] = height[rows[q]];
+            } else {
+                for (int32_t q = 0; q < nr0; ++q) key[q] = level[rows[q]];
+            }
+            std::vector<int32_t> cnt(depth[t] + 1, 0);
+            for (int32_t q = 0; q < nr0; ++q) ++cnt[key[q]];
+            int32_t acc = 0;
+            k0 = depth[t];
+            while (k0 > 0 && acc + cnt[k0 - 1] <= chain_max) { --k0; acc += cnt[k0]; }
+            const int nd = initial ? k0 + 1 : k0 + 2;
+            if (acc > 0 && depth[t] - nd >= chain_gain) {
+                new_depth = nd;
+                for (int32_t q = 0; q < nr0; ++q) if (key[q] >= k0) C.push_back(rows[q]);   // solve order = topological
+            }
+        }
+        const int32_t nC = (int32_t)C.size();
+        for (int32_t i = 0; i < nC; ++i) cidx[C[i]] = i;
+        // ---- levels of PkRow
+        std::vector<std::vector<PkRow>> lv(new_depth);
+        auto plain_row = [&](int32_t u) {
+            PkRow r; r.slot = loc[u]; r.invd = H.inv_diag[u];
+            for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
+                if (same(u, p)) { r.idx.push_back((uint16_t)loc[H.dep[p]]); r.val.push_back(H.val[p]); }
+            return r;
+        };
+        if (nC == 0) {
+            for (int32_t u : rows) lv[level[u]].push_back(plain_row(u));
+        } else {
+            // M = L_CC^-1 by rows:  M[c,:] = invd_c * (e_c - sum_{k in C} v_ck M[k,:])
+            std::vector<double> M((size_t)nC * nC, 0.0);
+            for (int32_t i = 0; i < nC; ++i) {
+                const int32_t u = C[i];
+                double* mi = M.data() + (size_t)i * nC;
+                mi[i] = 1.0;
+                for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) {
+                    if (!same(u, p) || cidx[H.dep[p]] < 0) continue;
+                    const int32_t k = cidx[H.dep[p]];
+                    const double v = H.val[p];
+                    const double* mk = M.data() + (size_t)k * nC;
+                    for (int32_t j = 0; j <= k; ++j) mi[j] -= v * mk[j];
+                }
+                const double d = H.inv_diag[u];
+                for (int32_t j = 0; j <= i; ++j) mi[j] *= d;
+            }
+            const bool initial = !H.subtrees_first;
+            const int lvB = initial ? 0 : k0 + 1;
+            for (int32_t i = 0; i < nC; ++i) {          // x_C = M t_C:  x = (0 - sum M t) * (-1)
+                PkRow r; r.slot = loc[C[i]]; r.invd = -1.0;
+                const double* mi = M.data() + (size_t)i * nC;
+                for (int32_t j = 0; j <= i; ++j) if (mi[j] != 0.0) { r.idx.push_back((uint16_t)(nr0 + j)); r.val.push_back(mi[j]); }
+                chain_entries += (int64_t)r.idx.size();
+                lv[lvB].push_back(std::move(r));
+            }
+            if (initial) {
+                for (int32_t u : rows) {
+                    if (cidx[u] >= 0) continue;
+                    int32_t l = 0;
+                    for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
+                        if (same(u, p) && cidx[H.dep[p]] < 0) l = std::max(l, lvl_r[H.dep[p]] + 1);
+                    lvl_r[u] = l;
+                    lv[1 + l].push_back(plain_row(u));
+                }
+            } else {
+                for (int32_t u : rows) {
+                    if (cidx[u] < 0) { lv[level[u]].push_back(plain_row(u)); continue; }
+                    PkRow r; r.slot = nr0 + cidx[u]; r.invd = 1.0;     // t_c = b_c - L_cR x_R
+                    for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
+                        if (same(u, p) && cidx[H.dep[p]] < 0) { r.idx.push_back((uint16_t)loc[H.dep[p]]); r.val.push_back(H.val[p]); }
+                    if (!r.idx.empty()) lv[k0].push_back(std::move(r));
+                }
+            }
+            ++n_collapsed; levels_before += depth[t]; levels_after += new_depth;
+        }
+        // ---- records and chunks
+        Packed P; P.t = (int32_t)t; P.last_used = 0; P.levels = new_depth;
+        P.slot_u.assign(nr0 + nC, -1); P.slot_src.assign(nr0 + nC, -1);
+        for (int32_t q = 0; q < nr0; ++q) {
+            const int32_t u = rows[q];
+            P.slot_u[q] = u;
+            if (cidx[u] < 0) P.slot_src[q] = u; else P.slot_src[nr0 + cidx[u]] = u;
+        }
         std::vector<uint16_t> seg_end, rec_rel;      // open chunk; rec_rel: record offsets (bytes) inside the records area
         std::vector<unsigned char> recs;
         auto dir_bytes = [](size_t nseg, size_t nslots) { return (4 + 2 * nseg + 2 * nslots + 7) / 8 * 8; };
@@ -496,44 +625,51 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
             rec_rel.push_back((uint16_t)recs.size());
             recs.insert(recs.end(), rec.begin(), rec.end());
         };
-        auto make_record = [&](const int32_t* us, int nrows, bool is_long) {
-            std::vector<int32_t> uloc(8, -1);
-            std::vector<uint16_t> start(8, 0), len(8, 0);
-            std::vector<double> invd(8, 0.0), val;
-            std::vector<uint16_t> idx;
-            for (int r = 0; r < nrows; ++r) {
-                const int32_t u = us[r];
-                uloc[r] = loc[u]; start[r] = (uint16_t)val.size(); invd[r] = H.inv_diag[u];
-                for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
-                    if (H.sub[H.dep[p]] == H.sub[u]) { val.push_back(H.val[p]); idx.push_back((uint16_t)loc[H.dep[p]]); }
-                len[r] = (uint16_t)(val.size() - start[r]);
-            }
-            const size_t ne = val.size();
-            std::vector<unsigned char> rec(kPkRecHeader + 8 * ne + (2 * ne + 7) / 8 * 8, 0);
+        auto make_record = [&](const PkRow* const* rs, int nrows, bool is_long) {
+            size_t ne = 0;
+            for (int r = 0; r < nrows; ++r) ne += rs[r]->val.size();
+            const size_t val0 = kPkRecHeader, idx0 = kPkRecHeader + 8 * ne;
+            std::vector<unsigned char> rec(idx0 + (2 * ne + 7) / 8 * 8, 0);
             int32_t* hdr = reinterpret_cast<int32_t*>(rec.data());
-            hdr[0] = (int32_t)ne; hdr[1] = is_long ? 1 : 0;
-            std::copy(uloc.begin(), uloc.end(), hdr + 2);
-            std::copy(start.begin(), start.end(), reinterpret_cast<uint16_t*>(rec.data() + 40));
-            std::copy(len.begin(), len.end(), reinterpret_cast<uint16_t*>(rec.data() + 56));
-            std::copy(invd.begin(), invd.end(), reinterpret_cast<double*>(rec.data() + 72));
-            if (ne) {
-                std::copy(val.begin(), val.end(), reinterpret_cast<double*>(rec.data() + kPkRecHeader));
-                std::copy(idx.begin(), idx.end(), reinterpret_cast<uint16_t*>(rec.data() + kPkRecHeader + 8 * ne));
+            int32_t* slot = hdr + 2;
+            uint16_t* voff = reinterpret_cast<uint16_t*>(rec.data() + 40);
+            uint16_t* ioff = reinterpret_cast<uint16_t*>(rec.data() + 56);
+            uint16_t* len = reinterpret_cast<uint16_t*>(rec.data() + 72);
+            double* invd = reinterpret_cast<double*>(rec.data() + 88);
+            double* val = reinterpret_cast<double*>(rec.data() + val0);
+            uint16_t* idx = reinterpret_cast<uint16_t*>(rec.data() + idx0);
+            hdr[0] = is_long ? 1 : 0; hdr[1] = (int32_t)ne;
+            size_t e = 0;
+            for (int r = 0; r < 8; ++r) {
+                slot[r] = -1; voff[r] = (uint16_t)(val0 / 8); ioff[r] = (uint16_t)(idx0 / 2); len[r] = 0; invd[r] = 0.0;
+                const PkRow* row = is_long ? rs[0] : (r < nrows ? rs[r] : nullptr);
+                if (!row) continue;
+                if (is_long && r > 0) {        // replicate row 0
+                    slot[r] = slot[0]; voff[r] = voff[0]; ioff[r] = ioff[0]; len[r] = len[0]; invd[r] = invd[0];
+                    continue;
+                }
+                slot[r] = row->slot; invd[r] = row->invd; len[r] = (uint16_t)row->val.size();
+                voff[r] = (uint16_t)((val0 + 8 * e) / 8); ioff[r] = (uint16_t)((idx0 + 2 * e) / 2);
+                std::copy(row->val.begin(), row->val.end(), val + e);
+                std::copy(row->idx.begin(), row->idx.end(), idx + e);
+                e += row->val.size();
             }
             return rec;
         };
-        for (int l = 0; l < depth[t]; ++l) {
-            std::vector<int32_t> longs, shorts;
-            for (int32_t u : by_level[l]) (loc_cnt[u] > kLongRowNnz ? longs : shorts).push_back(u);
+        for (int l = 0; l < new_depth; ++l) {
+            std::vector<const PkRow*> longs, shorts;
+            for (const PkRow& r : lv[l]) ((int)r.idx.size() > kLongRowNnz ? longs : shorts).push_back(&r);
+            std::stable_sort(longs.begin(), longs.end(), [](const PkRow* a, const PkRow* b) { return a->idx.size() > b->idx.size(); });
             bool first = true;
-            for (int32_t u : longs) { add_record(make_record(&u, 1, true), first); first = false; }
+            for (const PkRow* r : longs) { add_record(make_record(&r, 1, true), first); first = false; }
             for (size_t q = 0; q < shorts.size(); q += 8) {
                 add_record(make_record(shorts.data() + q, (int)std::min<size_t>(8, shorts.size() - q), false), first);
                 first = false;
             }
         }
         close_chunk();
-        if ((int64_t)rows.size() <= kPkWarpRows && P.bytes.size() == (size_t)kPkChunk && P.last_used <= (size_t)kPkWarpBlob) {
+        for (int32_t u : C) cidx[u] = -1;
+        if (nC == 0 && nr0 <= kPkWarpRows && P.bytes.size() == (size_t)kPkChunk && P.last_used <= (size_t)kPkWarpBlob) {
             P.bytes.resize((P.last_used + 15) / 16 * 16);
             kind[t] = 1;
             blobs.push_back(std::move(P));
@@ -548,33 +684,36 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     if (packs.empty() && blobs.empty()) return;
     // biggest first: CTAs are dispatched in index order
     std::stable_sort(packs.begin(), packs.end(), [](const Packed& a, const Packed& b) { return a.bytes.size() > b.bytes.size(); });
-    std::stable_sort(blobs.begin(), blobs.end(), [&](const Packed& a, const Packed& b) { return depth[a.t] > depth[b.t]; });
+    std::stable_sort(blobs.begin(), blobs.end(), [&](const Packed& a, const Packed& b) { return a.levels > b.levels; });
     std::vector<int64_t> chunk_off(1, 0), blob_off(1, 0), row_off(1, 0), ext_ptr(1, 0);
     std::vector<int32_t> prow_u, prow_src, prow_out, ext_dep;
     std::vector<double> ext_val;
     std::vector<unsigned char> stream, blob_bytes;
-    int64_t max_rows = 0;
-    auto add_rows = [&](int32_t t) {
-        for (int32_t u : members[t]) {
+    int64_t max_slots = 0;
+    auto add_slots = [&](const Packed& P) {
+        for (size_t q = 0; q < P.slot_u.size(); ++q) {
+            const int32_t u = P.slot_u[q], su = P.slot_src[q];
             prow_u.push_back(u);
-            prow_src.push_back(H.gather ? (*H.gather)[u] : u);
-            prow_out.push_back(H.out_perm ? (*H.out_perm)[u] : 0);
-            for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p)
-                if (H.sub[H.dep[p]] != H.sub[u]) { ext_dep.push_back(H.dep[p]); ext_val.push_back(H.val[p]); }
+            prow_out.push_back((u >= 0 && H.out_perm) ? (*H.out_perm)[u] : 0);
+            prow_src.push_back(su < 0 ? -1 : (H.gather ? (*H.gather)[su] : su));
+            if (su >= 0)
+                for (int64_t p = H.ptr[su]; p < H.ptr[su + 1]; ++p)
+                    if (!same(su, p)) { ext_dep.push_back(H.dep[p]); ext_val.push_back(H.val[p]); }
             ext_ptr.push_back((int64_t)ext_dep.size());
         }
         row_off.push_back((int64_t)prow_u.size());
+        max_slots = std::max<int64_t>(max_slots, (int64_t)P.slot_u.size());
     };
     for (const Packed& P : packs) {
         stream.insert(stream.end(), P.bytes.begin(), P.bytes.end());
         chunk_off.push_back((int64_t)(stream.size() / kPkChunk));
-        add_rows(P.t);
-        max_rows = std::max<int64_t>(max_rows, (int64_t)members[P.t].size());
+        add_slots(P);
     }
+    const int64_t cta_slots = max_slots;
     for (const Packed& P : blobs) {
         blob_bytes.insert(blob_bytes.end(), P.bytes.begin(), P.bytes.end());
         blob_off.push_back((int64_t)(blob_bytes.size() / 16));
-        add_rows(P.t);
+        add_slots(P);
     }
     S.pk_rows = (int64_t)prow_u.size();
     S.pk_has_ext = !ext_dep.empty();
@@ -585,13 +724,21 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     S.pk_row_off.upload(row_off); S.pk_prow_u.upload(prow_u); S.pk_prow_src.upload(prow_src); S.pk_prow_out.upload(prow_out);
     S.pk_ext_ptr.upload(ext_ptr); S.pk_ext_dep.upload(ext_dep); S.pk_ext_val.upload(ext_val);
     S.pk_w.alloc(S.pk_rows);
-    S.pk_smem = (size_t)kPkRing * kPkChunk + 64 + sizeof(double) * (size_t)max_rows;
+    if (getenv("CUADMM_YSOLVE_TIMELINE") && !packs.empty()) {   // debug: per-CTA globaltimer stamps of tri_packed_kernel
+        S.pk_timeline.alloc(4 * (int64_t)packs.size());
+        std::vector<long long> meta;
+        for (const Packed& P : packs) { meta.push_back((long long)(P.bytes.size() / kPkChunk)); meta.push_back((long long)P.slot_u.size()); meta.push_back(P.levels); }
+        S.pk_timeline_meta = meta;
+    }
+    S.pk_smem = (size_t)kPkRing * kPkChunk + 64 + sizeof(double) * (size_t)cta_slots;
     CUADMM_CUDA(cudaFuncSetAttribute((const void*)tri_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.pk_smem));
-    if (getenv("CUADMM_YSOLVE_VERBOSE"))
+    if (verbose)
         fprintf(stderr, "[ysolve] %s packed: %zu CTA subtrees in %lld chunks (largest %zu), %zu warp subtrees in %zu bytes, "
-                "%lld rows, %lld external entries, smem %zu\n", H.subtrees_first ? "fwd" : "bwd", packs.size(),
-                (long long)chunk_off.back(), packs.empty() ? (size_t)0 : packs[0].bytes.size() / kPkChunk, blobs.size(),
-                blob_bytes.size(), (long long)S.pk_rows, (long long)ext_ptr.back(), S.pk_smem);
+                "%lld slots, %lld external entries, smem %zu; chains collapsed in %lld subtrees (%lld -> %lld levels, %lld inverse entries)\n",
+                H.subtrees_first ? "fwd" : "bwd", packs.size(), (long long)chunk_off.back(),
+                packs.empty() ? (size_t)0 : packs[0].bytes.size() / kPkChunk, blobs.size(), blob_bytes.size(), (long long)S.pk_rows,
+                (long long)ext_ptr.back(), S.pk_smem, (long long)n_collapsed, (long long)levels_before, (long long)levels_after,
+                (long long)chain_entries);
 }
 
 static void upload_sweep(const HostSweep& H, TriSweep& S) {
@@ -900,6 +1047,22 @@ int cuadmm_ysolve(cuadmm_ysolve_t* ys, const double* d_rhs, double* d_y, void* s
         CUADMM_REQUIRE(ys && d_rhs && d_y, "null argument");
         DeviceGuard g(ys->device);
         ys->solve(d_rhs, d_y, (cudaStream_t)stream);
+    });
+}
+
+// debug: timeline[4*t..] = globaltimer stamps (start, after prologue, after levels, end) of CTA t of the
+// packed kernel of the last solve (which: 0 forward, 1 backward); meta[3*t..] = chunks, rows, depth.
+// Needs CUADMM_YSOLVE_TIMELINE=1 at create time.  Returns the CTA count through *n.
+int cuadmm_debug_ysolve_timeline(cuadmm_ysolve_t* ys, int which, long long* timeline, long long* meta, int64_t cap, int64_t* n) {
+    return guarded([&] {
+        CUADMM_REQUIRE(ys && n, "null argument");
+        DeviceGuard g(ys->device);
+        const cuadmm::TriSweep& S = which ? ys->bwd : ys->fwd;
+        *n = S.pk_timeline.n / 4;
+        if (!timeline || cap < *n || *n == 0) return;
+        CUADMM_CUDA(cudaDeviceSynchronize());
+        CUADMM_CUDA(cudaMemcpy(timeline, S.pk_timeline.p, sizeof(long long) * 4 * (size_t)*n, cudaMemcpyDeviceToHost));
+        if (meta) std::copy(S.pk_timeline_meta.begin(), S.pk_timeline_meta.end(), meta);
     });
 }
 

@@ -34,6 +34,8 @@ struct TriSweep {
     DevBuf<int64_t> pk_chunk_off, pk_blob_off, pk_row_off, pk_ext_ptr;
     DevBuf<int32_t> pk_prow_u, pk_prow_src, pk_prow_out, pk_ext_dep;
     DevBuf<double> pk_ext_val, pk_w;
+    DevBuf<long long> pk_timeline;            // debug (CUADMM_YSOLVE_TIMELINE)
+    std::vector<long long> pk_timeline_meta;
     size_t pk_smem = 0;
     bool pk_has_ext = false;
     int sub_depth = 0;
