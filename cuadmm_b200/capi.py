@@ -76,6 +76,7 @@ _sig("cuadmm_plan_start_indices", C.c_int64, vp, C.c_int, c_i64p)
 _sig("cuadmm_plan_maps", C.c_int, vp, c_i32p, c_i32p, c_i32p)
 _sig("cuadmm_plan_partition", C.c_int, vp, C.c_int, c_i32p, c_f64p)
 _sig("cuadmm_plan_set_jacobi", C.c_int, vp, C.c_double, C.c_int)
+_sig("cuadmm_plan_set_warm_start", C.c_int, vp, C.c_int)
 _sig("cuadmm_plan_last_ms", C.c_double, vp)
 _sig("cuadmm_plan_last_launches", C.c_int64, vp)
 _sig("cuadmm_project_psd", C.c_int, vp, vp, vp, vp)
@@ -143,6 +144,9 @@ class Plan:
 
     def set_jacobi(self, threshold, max_sweeps):
         _check(lib.cuadmm_plan_set_jacobi(self.h, threshold, max_sweeps))
+
+    def set_warm_start(self, enable):
+        _check(lib.cuadmm_plan_set_warm_start(self.h, 1 if enable else 0))
 
     def project_host(self, Xb):
         Xb = _f64(Xb)

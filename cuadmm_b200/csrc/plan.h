@@ -36,6 +36,10 @@ struct cuadmm_plan {
     cuadmm::DevBuf<int32_t> d_blk;
     cuadmm::DevBuf<uint8_t> d_pool;
 
+    // warm start of the Jacobi kernels: per block the orthonormal basis the last projection ended in
+    cuadmm::DevBuf<double> d_Q;
+    bool warm_start = true;
+    void reset_warm_start();
     double threshold = 1e-11;
     int max_sweeps = 40;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

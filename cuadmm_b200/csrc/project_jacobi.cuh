@@ -39,6 +39,7 @@ struct BlkDesc {
     int64_t w_off;        // offset of the block's eigenvalues in the debug output
     int32_t n;            // block size
     int32_t index;        // block index in blk order
+    int64_t q_off;        // offset of the block's n x n warm-start basis (shared-memory kernels only)
 };
 
 // Optional fused ADMM epilogue (src/solver.cu:652-675): with Xproj = Pi_+(Xb),
@@ -64,6 +65,7 @@ struct ProjArgs {
     int32_t* sweeps_out;    // optional (null): sweeps used, at desc.index
     double* scratch;        // global variant
     const int* done_flag;   // optional device flag: kernels return at once when *done_flag != 0
+    double* Q;              // optional (null): warm-start bases, n x n column-major at desc.q_off, read AND updated
     ProjEpilogue epi;
 };
 

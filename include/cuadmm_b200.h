@@ -96,6 +96,12 @@ double cuadmm_plan_last_ms(const cuadmm_plan* plan);
 int64_t cuadmm_plan_last_launches(const cuadmm_plan* plan);
 /* tuning: Jacobi convergence threshold on max |cos(g_p,g_q)| (default 1e-11), max sweeps */
 int cuadmm_plan_set_jacobi(cuadmm_plan* plan, double threshold, int max_sweeps);
+/* Warm start (default on; env CUADMM_JACOBI_WARM=0 turns it off): the plan keeps, per block, the
+ * orthonormal eigenbasis its last projection ended in and starts the next Jacobi from it, which is
+ * what makes successive ADMM iterates cheap (2-3 sweeps instead of 7-9).  The result is the same
+ * projection to rounding, but no longer bit-identical between two calls on the same input.
+ * enable = 0: forget the bases and project from cold every time; 1: forget the bases, keep warm starting. */
+int cuadmm_plan_set_warm_start(cuadmm_plan* plan, int enable);
 
 /* --------------------------------------------------------------------------
  * Sparse constraint operators.

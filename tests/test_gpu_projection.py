@@ -196,6 +196,7 @@ def test_device_pointer_entry_matches_host_entry():
     blk = [10, 33, 5]
     x = random_svec(blk, seed=2)
     p = cu.Plan(blk)
+    p.set_warm_start(False)          # cold Jacobi every call: the two entries must agree bit for bit
     ref = p.project_host(x)
     dx = torch.from_numpy(x).cuda(); dy = torch.empty_like(dx)
     s = torch.cuda.Stream()
@@ -219,3 +220,34 @@ def test_against_reference_cusolver_build(oref):
     lap = onp.project_svec(blk, x)
     assert np.linalg.norm(ours - lap) / np.linalg.norm(lap) < 1e-12
     assert np.linalg.norm(out_ref - lap) / np.linalg.norm(lap) < 1e-5
+
+
+def test_warm_start_matches_cold_and_oracle():
+    """The plan warm-starts Jacobi from the eigenbasis of its previous call.  Project a sequence of
+    slowly drifting inputs (as successive ADMM iterates are), then an unrelated one: every result must
+    match the LAPACK oracle as tightly as a cold plan does, and the sweep count must drop."""
+    blk = [6, 17, 33, 60, 60, 96, 128, 150]
+    rng = np.random.default_rng(5)
+    x = random_svec(blk, seed=11)
+    warm = cu.Plan(blk)
+    cold = cu.Plan(blk); cold.set_warm_start(False)
+    sweeps_warm, sweeps_cold = [], []
+    for it in range(6):
+        xi = x + (1e-3 * it) * random_svec(blk, seed=100 + it)
+        ow, _, sw = warm.project_eig_host(xi)
+        oc, _, sc = cold.project_eig_host(xi)
+        ref = onp.project_svec(blk, xi)
+        scale = np.abs(ref).max()
+        assert np.abs(ow - ref).max() <= 2e-13 * scale
+        assert np.abs(oc - ref).max() <= 2e-13 * scale
+        sweeps_warm.append(sw.max()); sweeps_cold.append(sc.max())
+    assert max(sweeps_warm[1:]) < min(sweeps_cold[1:]), (sweeps_warm, sweeps_cold)
+    y = random_svec(blk, seed=77)                      # unrelated input: still correct, just not faster
+    ow, _, _ = warm.project_eig_host(y)
+    ref = onp.project_svec(blk, y)
+    assert np.abs(ow - ref).max() <= 2e-13 * np.abs(ref).max()
+    z = np.zeros_like(y)                               # zero block keeps the stored basis valid
+    assert np.array_equal(warm.project_host(z), z)
+    ow, _, _ = warm.project_eig_host(x)
+    ref = onp.project_svec(blk, x)
+    assert np.abs(ow - ref).max() <= 2e-13 * np.abs(ref).max()
