@@ -72,15 +72,41 @@ __global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
         const int64_t gid = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
         const int64_t ngroups = (int64_t)main_blocks * kThreads / G;
         const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
-        for (int64_t i = gid; i < rows; i += ngroups) {
-            const int p0 = rowptr[i], p1 = rowptr[i + 1];
-            double r = 0.0;
-            if (p1 - p0 <= kLongRow) {
-                for (int p = p0 + sub; p < p1; p += G) r = fma(val[p], x[colind[p]], r);
+        // U rows per group in flight: the loads of one row are a chain of three dependent round trips
+        // (row pointer -> column/value -> x), and with ~2 entries per row there is nothing else to
+        // overlap them with, so independent rows are interleaved by hand.
+        constexpr int U = 4;
+        for (int64_t i0 = gid; i0 < rows; i0 += ngroups * U) {
+            int p0[U], p1[U];
+            bool mine[U];
+            double r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * ngroups;
+                p0[u] = 0; p1[u] = 0;
+                if (i < rows) { p0[u] = rowptr[i]; p1[u] = rowptr[i + 1]; }
+                mine[u] = i < rows && p1[u] - p0[u] <= kLongRow;      // long rows belong to the warps below
+                if (!mine[u]) p1[u] = p0[u];
             }
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) r += __shfl_xor_sync(gmask, r, o);
-            if (sub == 0 && p1 - p0 <= kLongRow) spmv_store(e, alpha, beta, y, i, r, acc0, acc1);
+            for (int u = 0; u < U; ++u) {
+                const int p = p0[u] + sub;
+                r[u] = 0.0;
+                if (p < p1[u]) r[u] = fma(val[p], x[colind[p]], 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                for (int p = p0[u] + sub + G; p < p1[u]; p += G) r[u] = fma(val[p], x[colind[p]], r[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) r[u] += __shfl_xor_sync(gmask, r[u], o);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * ngroups;
+                if (sub == 0 && mine[u]) spmv_store(e, alpha, beta, y, i, r[u], acc0, acc1);
+            }
         }
     } else {
         // long rows: one warp per row

@@ -221,19 +221,41 @@ __device__ __forceinline__ void pk_record(const unsigned char* rec, int lane, do
 }
 
 // w[g] = rhs[src[g]] - sum over the row's dependencies OUTSIDE its subtree (all final by now) of
-// val * x[dep]: one thread per packed row, so the subtree kernels start from a coalesced read.
-__global__ void __launch_bounds__(256) pk_gather_kernel(int64_t n_rows, const int32_t* __restrict__ prow_src,
-        const int64_t* __restrict__ ext_ptr, const int32_t* __restrict__ ext_dep, const double* __restrict__ ext_val,
-        const double* __restrict__ rhs, const double* __restrict__ x, double* __restrict__ w,
-        const int* __restrict__ done_flag) {
+// val * x[dep], so the subtree kernels start from a coalesced read.  One thread per packed row in
+// the first main_blocks CTAs; rows with many external entries (the collapsed chains at the top of
+// a subtree touch hundreds of ancestors) are left to the remaining CTAs, one warp per row.
+static constexpr int kPkHeavyExt = 8;
+
+__global__ void __launch_bounds__(256) pk_gather_kernel(int64_t n_rows, int main_blocks, const int32_t* __restrict__ heavy,
+        int n_heavy, const int32_t* __restrict__ prow_src, const int64_t* __restrict__ ext_ptr,
+        const int32_t* __restrict__ ext_dep, const double* __restrict__ ext_val, const double* __restrict__ rhs,
+        const double* __restrict__ x, double* __restrict__ w, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
-    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (g >= n_rows) return;
-    const int32_t src = prow_src[g];
-    double acc = src >= 0 ? rhs[src] : 0.0;        // src < 0: a slot that starts from zero (see pack_subtrees)
-    if (ext_ptr)
-        for (int64_t p = ext_ptr[g]; p < ext_ptr[g + 1]; ++p) acc = fma(-ext_val[p], x[ext_dep[p]], acc);
-    w[g] = acc;
+    if ((int)blockIdx.x < main_blocks) {
+        const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        if (g >= n_rows) return;
+        const int32_t src = prow_src[g];
+        double acc = src >= 0 ? rhs[src] : 0.0;        // src < 0: a slot that starts from zero (see pack_subtrees)
+        if (ext_ptr) {
+            const int64_t p0 = ext_ptr[g], p1 = ext_ptr[g + 1];
+            if (p1 - p0 > kPkHeavyExt) return;
+            for (int64_t p = p0; p < p1; ++p) acc = fma(-ext_val[p], x[ext_dep[p]], acc);
+        }
+        w[g] = acc;
+    } else {
+        const int lane = threadIdx.x & 31;
+        const int hw = ((int)blockIdx.x - main_blocks) * 8 + (threadIdx.x >> 5);
+        if (hw >= n_heavy) return;
+        const int64_t g = heavy[hw];
+        double acc = 0.0;
+        for (int64_t p = ext_ptr[g] + lane; p < ext_ptr[g + 1]; p += 32) acc = fma(ext_val[p], x[ext_dep[p]], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const int32_t src = prow_src[g];
+            w[g] = (src >= 0 ? rhs[src] : 0.0) - acc;
+        }
+    }
 }
 
 // walk the segments of one chunk (resident in shared memory) with NW warps; WARP = the chunk belongs to one warp
@@ -366,8 +388,10 @@ static int launch_subtrees(const TriSweep& S, const double* rhs, const int32_t* 
                            const int32_t* out_perm, const int* done, cudaStream_t st, const SweepStreams& ss) {
     int launches = 0;
     if (S.pk_rows > 0) {
-        pk_gather_kernel<<<(unsigned)((S.pk_rows + 255) / 256), 256, 0, st>>>(S.pk_rows, S.pk_prow_src.p,
-            S.pk_has_ext ? S.pk_ext_ptr.p : nullptr, S.pk_ext_dep.p, S.pk_ext_val.p, rhs, x, S.pk_w.p, done);
+        const int main_blocks = (int)((S.pk_rows + 255) / 256);
+        pk_gather_kernel<<<(unsigned)(main_blocks + (S.pk_n_heavy + 7) / 8), 256, 0, st>>>(S.pk_rows, main_blocks, S.pk_heavy.p,
+            (int)S.pk_n_heavy, S.pk_prow_src.p, S.pk_has_ext ? S.pk_ext_ptr.p : nullptr, S.pk_ext_dep.p, S.pk_ext_val.p, rhs, x,
+            S.pk_w.p, done);
         ++launches;
     }
     const bool fork = S.n_sub_warp > 0 && (S.n_sub_pack > 0 || S.n_sub_cta > 0);
@@ -724,6 +748,11 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     S.pk_row_off.upload(row_off); S.pk_prow_u.upload(prow_u); S.pk_prow_src.upload(prow_src); S.pk_prow_out.upload(prow_out);
     S.pk_ext_ptr.upload(ext_ptr); S.pk_ext_dep.upload(ext_dep); S.pk_ext_val.upload(ext_val);
     S.pk_w.alloc(S.pk_rows);
+    std::vector<int32_t> heavy;
+    for (int64_t g = 0; g < S.pk_rows; ++g) if (ext_ptr[g + 1] - ext_ptr[g] > kPkHeavyExt) heavy.push_back((int32_t)g);
+    S.pk_n_heavy = (int64_t)heavy.size();
+    if (heavy.empty()) heavy.push_back(0);
+    S.pk_heavy.upload(heavy);
     if (getenv("CUADMM_YSOLVE_TIMELINE") && !packs.empty()) {   // debug: per-CTA globaltimer stamps of tri_packed_kernel
         S.pk_timeline.alloc(4 * (int64_t)packs.size());
         std::vector<long long> meta;
@@ -734,10 +763,10 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     CUADMM_CUDA(cudaFuncSetAttribute((const void*)tri_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.pk_smem));
     if (verbose)
         fprintf(stderr, "[ysolve] %s packed: %zu CTA subtrees in %lld chunks (largest %zu), %zu warp subtrees in %zu bytes, "
-                "%lld slots, %lld external entries, smem %zu; chains collapsed in %lld subtrees (%lld -> %lld levels, %lld inverse entries)\n",
+                "%lld slots, %lld external entries (%lld heavy rows), smem %zu; chains collapsed in %lld subtrees (%lld -> %lld levels, %lld inverse entries)\n",
                 H.subtrees_first ? "fwd" : "bwd", packs.size(), (long long)chunk_off.back(),
                 packs.empty() ? (size_t)0 : packs[0].bytes.size() / kPkChunk, blobs.size(), blob_bytes.size(), (long long)S.pk_rows,
-                (long long)ext_ptr.back(), S.pk_smem, (long long)n_collapsed, (long long)levels_before, (long long)levels_after,
+                (long long)ext_ptr.back(), (long long)S.pk_n_heavy, S.pk_smem, (long long)n_collapsed, (long long)levels_before, (long long)levels_after,
                 (long long)chain_entries);
 }
 

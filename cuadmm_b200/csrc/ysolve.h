@@ -32,7 +32,8 @@ struct TriSweep {
     int64_t n_sub_pack = 0, n_sub_warp = 0, pk_rows = 0;
     DevBuf<unsigned char> pk_stream, pk_blobs;
     DevBuf<int64_t> pk_chunk_off, pk_blob_off, pk_row_off, pk_ext_ptr;
-    DevBuf<int32_t> pk_prow_u, pk_prow_src, pk_prow_out, pk_ext_dep;
+    DevBuf<int32_t> pk_prow_u, pk_prow_src, pk_prow_out, pk_ext_dep, pk_heavy;
+    int64_t pk_n_heavy = 0;      // rows with many external entries: one warp each in pk_gather_kernel
     DevBuf<double> pk_ext_val, pk_w;
     DevBuf<long long> pk_timeline;            // debug (CUADMM_YSOLVE_TIMELINE)
     std::vector<long long> pk_timeline_meta;
