@@ -2,6 +2,8 @@
 // mma.sync.m8n8k4.f64 (tcgen05 has no f64 kind; DMMA via mma.sync is the FP64 tensor path on
 // sm_100a), operands staged in shared memory.
 #include "dense.h"
+#include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace cuadmm {
@@ -230,8 +232,20 @@ __global__ void transpose_kernel(int64_t n, const double* __restrict__ in, doubl
     }
 }
 
+// which 64 x 64 tiles of a row-major r x r matrix hold a non-zero
+__global__ void tile_occupancy_kernel(int64_t r, int nt, const double* __restrict__ A, int* __restrict__ flags) {
+    const int I = blockIdx.y, J = blockIdx.x;
+    int any = 0;
+    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+        const int64_t i = (int64_t)I * 64 + e / 64, j = (int64_t)J * 64 + e % 64;
+        if (i < r && j < r && A[i * r + j] != 0.0) any = 1;
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) flags[I * nt + J] = 1;
+}
+
 void build_dense_tail(const SymCsc& C, const CholFactor& F, int64_t n_lead, int64_t r,
-                      DevBuf<double>& tail_inv, DevBuf<double>& tail_inv_t, int64_t* n_deficient) {
+                      DevBuf<double>& tail_inv, DevBuf<double>& tail_inv_t, int64_t* n_deficient,
+                      std::vector<int>* tile_flags) {
     cudaStream_t st = 0;
     // S <- M22 (both triangles)
     DevBuf<double> S(r * r);
@@ -293,6 +307,23 @@ void build_dense_tail(const SymCsc& C, const CholFactor& F, int64_t n_lead, int6
     transpose_kernel<<<grid, block, 0, st>>>(r, tail_inv_t.p, tail_inv.p);
     CUADMM_CUDA(cudaGetLastError());
     CUADMM_CUDA(cudaStreamSynchronize(st));
+    // which 64 x 64 tiles of L22^-1 hold anything: the GEMVs skip the empty ones
+    {
+        const int nt = (int)((r + 63) / 64);
+        DevBuf<int> flags((int64_t)nt * nt);
+        flags.zero(st);
+        tile_occupancy_kernel<<<dim3(nt, nt), 256, 0, st>>>(r, nt, tail_inv.p, flags.p);
+        std::vector<int> h((size_t)nt * nt);
+        flags.download(h.data(), (int64_t)h.size(), st);
+        CUADMM_CUDA(cudaStreamSynchronize(st));
+        if (getenv("CUADMM_YSOLVE_VERBOSE")) {
+            int64_t lower = 0, used = 0;
+            for (int I = 0; I < nt; ++I) for (int J = 0; J <= I; ++J) { ++lower; used += h[(size_t)I * nt + J]; }
+            fprintf(stderr, "[ysolve] dense tail %lld: %lld of %lld lower 64x64 tiles of L22^-1 are non-zero (%.1f%%)\n",
+                    (long long)r, (long long)used, (long long)lower, 100.0 * (double)used / (double)lower);
+        }
+        if (tile_flags) tile_flags->swap(h);
+    }
 }
 
 }  // namespace cuadmm

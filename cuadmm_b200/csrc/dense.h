@@ -20,6 +20,7 @@ void trtri_lower(cudaStream_t st, int64_t n, const double* L, int64_t ldl, const
 
 // y-solve: dense trailing block.  tail_inv = row-major L22^-1, tail_inv_t = row-major L22^-T.
 void build_dense_tail(const SymCsc& Cperm, const CholFactor& F, int64_t n_lead, int64_t n_tail,
-                      DevBuf<double>& tail_inv, DevBuf<double>& tail_inv_t, int64_t* n_deficient = nullptr);
+                      DevBuf<double>& tail_inv, DevBuf<double>& tail_inv_t, int64_t* n_deficient = nullptr,
+                      std::vector<int>* tile_flags = nullptr);   // nt x nt, row-major, of tail_inv (nt = ceil(n_tail / 64))
 
 }  // namespace cuadmm

@@ -360,10 +360,14 @@ __global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t
     }
 }
 
-// dense tail: out[i] = sum_j T[i, j] * in[j] for a row-major r x r matrix of which only the
-// lower (lower=true) or upper triangle is non-zero.  One warp per row, coalesced.
+// dense tail: out[i] = sum_j T[i, j] * in[j] for a row-major r x r triangular matrix (L22^-1 or its
+// transpose).  One warp per row, coalesced; only the 64-column tiles listed for the row's tile row
+// are read (tile_ptr / tile_col: per tile row, runs of consecutive non-empty tiles as column
+// ranges): the inverse of the trailing factor block inherits
+// the block structure of the separators it came from and is often half empty.
 __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double* __restrict__ T, const double* __restrict__ in,
-                                                        double* out, int lower, double* out_scatter,
+                                                        double* out, const int32_t* __restrict__ tile_ptr,
+                                                        const int32_t* __restrict__ tile_col, double* out_scatter,
                                                         const int32_t* __restrict__ out_perm, int64_t perm_base,
                                                         const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
@@ -371,9 +375,13 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= r) return;
     const double* Ti = T + row * r;
-    const int64_t j0 = lower ? 0 : row, j1 = lower ? row + 1 : r;
+    const int I = (int)(row >> 6);
     double acc = 0.0;
-    for (int64_t j = j0 + lane; j < j1; j += 32) acc = fma(Ti[j], in[j], acc);
+    for (int t = tile_ptr[I]; t < tile_ptr[I + 1]; ++t) {      // runs of consecutive non-empty tiles: [first, last) columns
+        const int64_t j1 = min((int64_t)tile_col[2 * t + 1], r);
+#pragma unroll 4
+        for (int64_t j = (int64_t)tile_col[2 * t] + lane; j < j1; j += 32) acc = fma(Ti[j], in[j], acc);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -1018,7 +1026,27 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
     // ---- dense tail: S = M22 - L21 L21^T, Cholesky, explicit inverse (all on the device)
     if (n_tail > 0) {
         int64_t tail_def = 0;
-        build_dense_tail(C, F, n_lead, n_tail, Y->tail_inv, Y->tail_inv_t, &tail_def);
+        std::vector<int> flags;
+        build_dense_tail(C, F, n_lead, n_tail, Y->tail_inv, Y->tail_inv_t, &tail_def, &flags);
+        const int nt = (int)((n_tail + 63) / 64);
+        std::vector<int32_t> tp(1, 0), tc, tpt(1, 0), tct;
+        auto add_runs = [&](std::vector<int32_t>& ptr, std::vector<int32_t>& col, int J0, int J1, auto used) {
+            for (int J = J0; J < J1;) {
+                if (!used(J)) { ++J; continue; }
+                int E = J;
+                while (E < J1 && used(E)) ++E;
+                col.push_back(J * 64); col.push_back(E * 64);
+                J = E;
+            }
+            ptr.push_back((int32_t)(col.size() / 2));
+        };
+        for (int I = 0; I < nt; ++I) {
+            add_runs(tp, tc, 0, I + 1, [&](int J) { return flags[(size_t)I * nt + J] != 0; });       // L22^-1: lower
+            add_runs(tpt, tct, I, nt, [&](int J) { return flags[(size_t)J * nt + I] != 0; });       // its transpose: upper
+        }
+        if (tc.empty()) tc.assign(2, 0);
+        if (tct.empty()) tct.assign(2, 0);
+        Y->tail_tptr.upload(tp); Y->tail_tcol.upload(tc); Y->tail_tptr_t.upload(tpt); Y->tail_tcol_t.upload(tct);
         Y->n_deficient += tail_def;
         Y->tail_tmp.alloc(n_tail);
     }
@@ -1050,8 +1078,10 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
     if (n_tail > 0) {
         const int blocks = (int)((n_tail + 7) / 8);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
-        tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tail_tmp.p, 1, nullptr, nullptr, 0, done_flag);
-        tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tail_tmp.p, x.p + n_lead, 0, d_y_, perm.p, n_lead, done_flag);
+        tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tail_tmp.p, tail_tptr.p, tail_tcol.p,
+                                                 nullptr, nullptr, 0, done_flag);
+        tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tail_tmp.p, x.p + n_lead, tail_tptr_t.p, tail_tcol_t.p,
+                                                 d_y_, perm.p, n_lead, done_flag);
         CUADMM_CUDA(cudaGetLastError());
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y

@@ -62,6 +62,7 @@ struct cuadmm_ysolve_s {
     cuadmm::DevBuf<double> x;          // backward result (permuted order)
     // dense tail: inverse of the trailing Cholesky block, row-major lower and its transpose
     cuadmm::DevBuf<double> tail_inv, tail_inv_t, tail_tmp;
+    cuadmm::DevBuf<int32_t> tail_tptr, tail_tcol, tail_tptr_t, tail_tcol_t;   // non-empty 64-column tiles per tile row (CSR)
     cuadmm::DevBuf<double> d_rhs, d_y; // staging for the host entry
     std::vector<int32_t> h_perm;
     const int* done_flag = nullptr;
