@@ -88,6 +88,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the projection stage from the committed ncu --set full
+    capture (profiles/ncu_traffic_r01.json); only valid for the workload it was taken on, else None"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    try:
+        d = json.load(open(p))
+        if d["workload"]["nblk"] == args.nblk and d["workload"]["con"] == args.con and args.gpus == 1:
+            st = d["projection_stage"]
+            return int(st["dram_bytes_read"] + st["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -263,7 +277,9 @@ def run_ours(args):
             "roofline": {"kernel": "proj_jacobi_kernel (fused svec->smat, one-sided Jacobi eig, clamp, rebuild, smat->svec, S/SmC "
                                    "epilogue; all size classes of one projection stage)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": hbm_src, "alg_bytes_per_launch": alg_bytes,
+                         "traffic": ncu_traffic(args), "traffic_source": "profiles/ncu_traffic_r01.json (ncu --set full, "
+                         "dram__bytes_read.sum + dram__bytes_write.sum summed over the stage's three launches)",
+                         "peak_source": hbm_src, "alg_bytes_per_launch": alg_bytes,
                          "launch_ms": proj_ms,
                          "note": "latency/issue-bound Jacobi kernel, neither HBM- nor tensor-bound (SURVEY 8d): "
                                  "F_alg=(20/3)sum n^3 = %.3g flop -> %.3f TFLOP/s vs 35.5 TFLOP/s measured cuBLAS DGEMM"
