@@ -34,11 +34,27 @@ def parse_args():
     ap.add_argument("--nblk", type=int, default=2000)
     ap.add_argument("--con", type=int, default=700000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2b", choices=["c2b", "c3", "c4"],
+                    help="c2b (default, BASELINE.json configs[1]); c3 = max-cut n=4000 (configs[2]); c4 = 10k mixed "
+                         "blocks {10,50,200,800}, m=1e6 (configs[3], the multi-GPU scaling configuration)")
     return ap.parse_args()
 
 
 def workload(args):
-    from cuadmm_b200.synthetic import c2b_blocks, chain_sdp
+    from cuadmm_b200.synthetic import c2b_blocks, chain_sdp, maxcut_sdp, c4_blocks, random_sdp
+    if args.workload == "c3":
+        P = maxcut_sdp(4000, p=0.01, seed=0)
+        return P, {"workload": "C3 max-cut SDP: one dense PSD block n=4000, G(n, 0.01) seed 0, m=n diagonal constraints, "
+                               "sGS-ADMM iteration", "nblk": 1, "vec_len": int(P["vec_len"]), "con_num": int(P["con_num"]),
+                   "nnz_A": int(len(P["vals"])), "l2": "one 128 MB dense block per n x n operand: exceeds the 126 MB L2"}
+    if args.workload == "c4":
+        blk = c4_blocks(seed=0)
+        m = args.con if args.con != 700000 else 1000000
+        P = random_sdp(blk, m, seed=0)
+        return P, {"workload": "C4 synthetic multi-block SDP: 10,000 blocks {10: 6000, 50: 3000, 200: 900, 800: 100} shuffled "
+                               "(seed 0), m=%d constraints with 1+Poisson(4) non-zeros at random svec positions of <= 2 blocks, sGS-ADMM iteration" % m, "nblk": int(len(blk)),
+                   "vec_len": int(P["vec_len"]), "con_num": int(P["con_num"]), "nnz_A": int(len(P["vals"])),
+                   "l2": "svec vectors of 434 MB each: far beyond the 126 MB L2"}
     blk = c2b_blocks(args.nblk, 6, 60, 0)
     P = chain_sdp(blk, args.con, seed=0)
     cfg = {"workload": "C2b synthetic moment-relaxation SDP: %d PSD blocks n~U{6..60} (seed 0), m=%d chain-structured "
@@ -94,7 +110,7 @@ def ncu_traffic(args):
     p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
     try:
         d = json.load(open(p))
-        if d["workload"]["nblk"] == args.nblk and d["workload"]["con"] == args.con and args.gpus == 1:
+        if args.workload == "c2b" and d["workload"]["nblk"] == args.nblk and d["workload"]["con"] == args.con and args.gpus == 1:
             st = d["projection_stage"]
             return int(st["dram_bytes_read"] + st["dram_bytes_write"])
     except Exception:
@@ -287,6 +303,16 @@ def run_ours(args):
                          "fp64_frac_of_dgemm_peak": f_alg / (proj_ms * 1e-3) / 1e12 / 35.5},
             "stage_ms_per_iter": {"projection": proj_ms, "ysolve_x2": prof["ysolve_ms"] / nprof, "spmv_and_rest": prof["other_ms"] / nprof},
             "ysolve": ys, "init_s": t_init}
+    if args.workload != "c2b":
+        # C3 / C4: the projection is dominated by the large blocks (n > 168), i.e. by sym_gemm_kernel, the FP64
+        # tensor-core (DMMA) product of the sign iteration: tensor-bound, F_alg = (20/3) n^3 per block
+        line["roofline"] = {"kernel": "projection stage: sym_gemm_kernel (FP64 DMMA sign iteration, blocks n > 168) + proj_jacobi_kernel",
+                            "bound": "tensor", "achieved": f_alg / world / (proj_ms * 1e-3) / 1e12, "peak": 35.5, "unit": "TFLOP/s",
+                            "frac": f_alg / world / (proj_ms * 1e-3) / 1e12 / 35.5, "traffic": None,
+                            "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool's B200 (gpurun_out/probe.json, round 1); "
+                                           "MEASURED_PEAKS.json holds no FP64 figure",
+                            "alg_flop_per_launch": f_alg / world, "launch_ms": proj_ms,
+                            "note": "the sign iteration executes ~35 symmetric products of n^3 flop each (~5x F_alg)"}
     if not args.no_cpu_baseline and args.gpus == 1:
         cores = os.cpu_count() or 1
         threads = min(30, cores)

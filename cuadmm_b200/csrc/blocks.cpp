@@ -99,11 +99,15 @@ void BlockLayout::maps(int32_t* map_B, int32_t* map_M1, int32_t* map_M2) const {
 }
 
 double BlockLayout::eig_cost(int n) {
-    // Jacobi regime: ~sweeps * n^3 with a per-block floor; dense regime: ~(20/3) n^3 at
-    // much higher throughput.  Calibrated coarsely; only ratios matter for the LPT split.
+    // Calibrated on B200 (profiles/jacobi_tuning_r01.md, profiles/dense_probe_r01.json); unit = 1e-7 us,
+    // only ratios matter for the LPT split.
+    //   Jacobi regime (n <= 168): ~3e-6 us * n^3 per block at full-GPU batches (warm-started sweeps) + floor;
+    //   dense regime: the sign iteration runs ~35 symmetric tile products; a block costs
+    //   T(T+1)/2 tiles (T = ceil(n/128)) x n deep, ~0.06 us per tile per unit of depth.
     const double nn = (double)n;
-    if (n <= 168) return 2.0e3 + 60.0 * nn * nn * nn;
-    return 4.0e6 + 9.0 * nn * nn * nn;
+    if (n <= 168) return 2.0e3 + 30.0 * nn * nn * nn;
+    const double T = (double)((n + 127) / 128);
+    return 6.0e5 * (0.5 * T * (T + 1.0)) * nn;
 }
 
 void BlockLayout::partition(int nparts, int32_t* owner, double* part_cost) const {

@@ -2,24 +2,32 @@
 //
 // Replaces cusolverDnXsyevd + diag scale + cublasDgemm for the reference's "large" blocks
 // (src/solver.cu:540-564, 600-644).  A full eigendecomposition is not needed to project: with the
-// matrix sign function U = sign(A),   Pi_+(A) = (A + U A) / 2.   U is computed by the Newton-Schulz
-// iteration  X <- X (3 I - X^2) / 2,  X_0 = A / ||A||_F  (spectrum in [-1, 1]; monotone on it, so no
-// eigenvalue is ever pushed towards 0 and the conditioning of sign() is that of A itself — a scaled
-// variant that maps the top of the spectrum onto a worst-case lower bound was measured to lose 5+
-// digits).  Convergence is quadratic; every step accumulates ||X^2 - I||_F^2 in its first product and
-// a block whose residual fell below 1e-14 is frozen (its later products degrade to copies), at most
-// 60 steps.  Eigenvalues with |lambda| < ~1e-10 ||A||_F may stay unconverged; they contribute less
-// than |lambda| to the projection.  All iterates are polynomials in A, hence symmetric: every product
-// is computed on the lower tile triangle only and mirrored (n^3 flop each), and every flop is a dense
-// DMMA contraction (mma.sync.m8n8k4.f64 — tcgen05 has no f64 kind), batched over all large blocks of
-// the plan.  One-stage tridiagonalisation would be half BLAS-2 and HBM-bound; this is not.
+// matrix sign function U = sign(A),   Pi_+(A) = (A + U A) / 2.   U is the limit of an odd polynomial
+// iteration  X <- p_k(X) = X (a_k I + b_k X^2 + c_k X^4)  started from X_0 = A / s, s >= ||A||_2:
+//   * scale: A_0 = A / ||A||_F; the first product A_0^2 is needed anyway and gives the sharper bound
+//     s = ||A_0^2||_F^(1/2) >= ||A_0||_2 for free (its coefficients are folded into step 0);
+//   * steps 0..6: degree-5 polynomials that are minimax-optimal for the sign function on [l_k, 1]
+//     (each maps [l_k, 1] into [l_{k+1}, 1] with the largest possible l_{k+1}; l_0 = 1e-4 -> 0.944 in seven
+//     steps, slope 4.26 at 0 against 1.5 for Newton-Schulz; table from scripts/sign_poly_table.py);
+//     p_k <= 1 on [0, 1] and p_k(x) >= x on [0, l_k], so smaller eigenvalues are never pushed back and
+//     the conditioning of sign() never gets worse than that of the scaled input — accuracy stays ~1e-14;
+//   * then the cubically convergent Newton-Schulz polynomial (15 x - 10 x^3 + 3 x^5) / 8 until
+//     ||X^2 - I||_F^2 < 1e-10 (the step after is ~1e-30) or the residual stagnates (exact or tiny zero
+//     eigenvalues: what is left unresolved contributes less than its own magnitude, < 1e-10 ||A||).
+// A block that is done is frozen (its later products degrade to copies / early exits).  All iterates
+// are polynomials in A, hence symmetric: every product is computed on the lower tile triangle only and
+// mirrored (n^3 flop each), and every flop is a dense DMMA contraction (mma.sync.m8n8k4.f64 — tcgen05
+// has no f64 kind), batched over all large blocks of the plan: 3 products per step, ~30 for a random
+// symmetric matrix (the plain Newton-Schulz iteration this replaced needed ~70).  One-stage
+// tridiagonalisation would be half BLAS-2 and HBM-bound; this is not.
 #include "plan.h"
 #include <algorithm>
 #include <cmath>
 
 namespace cuadmm {
 
-static constexpr int SG_M = 128, SG_N = 128, SG_K = 16, SG_PAD = 4, SG_THREADS = 256;
+static constexpr int SG_M = 128, SG_N = 128, SG_K = 16, SG_PAD = 4, SG_THREADS = 256, SG_STAGES = 4;
+static constexpr size_t SG_SMEM = sizeof(double) * SG_STAGES * SG_K * ((SG_M + SG_PAD) + (SG_N + SG_PAD));
 
 struct DenseDesc {
     int64_t off;        // element offset of the block in every n x n pool
@@ -27,6 +35,17 @@ struct DenseDesc {
     int32_t n;
     int32_t pad;
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sa), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -38,23 +57,56 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // are mirrored into the upper triangle.  128 x 128 x 16 tiles, 8 warps (4 x 2), warp tile 32 x 64 =
 // 4 x 8 DMMA tiles, double-buffered shared memory, row stride == 4 (mod 16) for conflict-free
 // fragment loads.  B is read through its transpose (B symmetric) so both operand loads are coalesced.
+// Per-block step-0 scale: alpha *= sc^pa, gamma *= sc^pg with sc = ||A_0^2||_F^(-1/2) read from
+// (res base)[0] (pa = pg = 0 otherwise).
+struct SignStep {
+    int mode;        // 0 plain; 1 X2 = X X, residual ||X2 - I||_F^2 -> res[k]; 3 same, but ||X2||_F^2 -> res[k] (step 0);
+                     // 2 middle product (frozen: skip); 4 last product of a step (frozen: copy A -> C)
+    int k;           // step index (residual slot)
+    int pa, pg;      // powers of the step-0 scale applied to alpha / gamma
+    int stag_from;   // residual stagnation may freeze a block once k - 1 >= stag_from
+};
+
+__device__ __forceinline__ bool sign_frozen(const double* __restrict__ res, int k, double tolsq, int stag_from) {
+    // res[j] = ||X_j^2 - I||_F^2 for j >= 1 (res[0] holds the step-0 scale); a frozen block carries its last
+    // residual forward, so it stays frozen
+    if (k < 2) return false;
+    const double r1 = res[k - 1];
+    if (r1 < tolsq) return true;
+    if (k - 1 >= stag_from && k >= 3) {
+        const double r0 = res[k - 2];
+        if (fabs(r0 - r1) <= 1e-13 * r1) return true;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* __restrict__ desc,
         const double* __restrict__ Ap, const double* __restrict__ Bp, double* Cp, const double* __restrict__ Dp,
         double alpha, double dshift, double gamma, const int* __restrict__ done_flag,
-        int mode, const double* __restrict__ res_prev, double* res_cur, int res_stride, double tolsq) {
-    // mode 1: first product of a step  (C = 1.5 I - 0.5 X X; accumulates ||X X - I||_F^2 into res_cur)
-    // mode 2: second product of a step (C = X Y), a frozen block copies X instead
-    // mode 0: plain
+        SignStep st, double* res_all, int res_stride, double tolsq) {
     if (done_flag && *done_flag) return;
+    const int mode = st.mode;
+    double* res = res_all ? res_all + (size_t)blockIdx.y * res_stride : nullptr;
     bool frozen = false;
-    if (mode != 0 && res_prev) frozen = res_prev[blockIdx.y * res_stride] < tolsq;
-    if (mode == 1 && frozen) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) res_cur[blockIdx.y * res_stride] = res_prev[blockIdx.y * res_stride];
+    if (mode != 0) frozen = sign_frozen(res, st.k, tolsq, st.stag_from);
+    if ((mode == 1 || mode == 3) && frozen) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) res[st.k] = res[st.k - 1];
         return;
+    }
+    if (mode == 2 && frozen) return;
+    if (st.pa | st.pg) {
+        const double f2 = res[0];                    // ||A_0^2||_F^2
+        const double sc = f2 > 0.0 ? rsqrt(sqrt(f2)) : 0.0;
+        double pw = 1.0;
+        for (int i = 0; i < st.pa; ++i) pw *= sc;
+        alpha *= pw;
+        pw = 1.0;
+        for (int i = 0; i < st.pg; ++i) pw *= sc;
+        gamma *= pw;
     }
     extern __shared__ double sg_smem[];
     double (*As)[SG_K][SG_M + SG_PAD] = reinterpret_cast<double (*)[SG_K][SG_M + SG_PAD]>(sg_smem);
-    double (*Bs)[SG_K][SG_N + SG_PAD] = reinterpret_cast<double (*)[SG_K][SG_N + SG_PAD]>(sg_smem + 2 * SG_K * (SG_M + SG_PAD));
+    double (*Bs)[SG_K][SG_N + SG_PAD] = reinterpret_cast<double (*)[SG_K][SG_N + SG_PAD]>(sg_smem + SG_STAGES * SG_K * (SG_M + SG_PAD));
     const DenseDesc d = desc[blockIdx.y];
     const int n = d.n;
     const int T = (n + SG_M - 1) / SG_M;
@@ -73,7 +125,7 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
 
-    if (mode == 2 && frozen) {
+    if (mode == 4 && frozen) {
         // converged block: X_{k+1} = X_k (tile copy, mirrored like the product)
         for (int e = tid; e < SG_M * SG_N; e += SG_THREADS) {
             const int gm = m0 + e % SG_M, gn = n0 + e / SG_M;
@@ -91,31 +143,50 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
+    // Operand staging: SG_STAGES-deep cp.async ring (global -> shared without a register round trip, zero
+    // fill outside the matrix through the src-size operand), one __syncthreads per k-tile.
+    // 16-byte copies when every column of the block is 16-byte aligned, 8-byte copies otherwise.
+    const bool v16 = ((n & 1) == 0) && ((d.off & 1) == 0);
     auto load_tiles = [&](int buf, int k0) {
-        // A tile 128 (m) x 16 (k): element (mm, kk) at A[m0+mm + (k0+kk) ld]   (coalesced along m)
+        if (v16) {
+            // A tile 128 (m) x 16 (k): element (mm, kk) at A[m0+mm + (k0+kk) ld] (contiguous along m); same for B
+            // through its transpose: B(kk, nn) = B(nn, kk) at B[n0+nn + (k0+kk) ld]
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int e = tid + t * SG_THREADS;
-            const int mm = e % SG_M, kk = e / SG_M;
-            const int gm = m0 + mm, gk = k0 + kk;
-            As[buf][kk][mm] = (gm < n && gk < n) ? A[gm + gk * ld] : 0.0;
-        }
-        // B tile 16 (k) x 128 (n): B(kk, nn) = B(nn, kk) (symmetric) at B[n0+nn + (k0+kk) ld]
+            for (int t = 0; t < 4; ++t) {
+                const int e = tid + t * SG_THREADS;            // 1024 16-byte chunks per operand
+                const int mm = (e & 63) * 2, kk = e >> 6;
+                const int gk = k0 + kk;
+                const int gm = m0 + mm, gn = n0 + mm;
+                const bool oka = gm < n && gk < n, okb = gn < n && gk < n;
+                cp_async16(&As[buf][kk][mm], oka ? A + gm + gk * ld : A, oka ? 16 : 0);
+                cp_async16(&Bs[buf][kk][mm], okb ? B + gn + gk * ld : B, okb ? 16 : 0);
+            }
+        } else {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int e = tid + t * SG_THREADS;
-            const int nn = e % SG_N, kk = e / SG_N;
-            const int gn = n0 + nn, gk = k0 + kk;
-            Bs[buf][kk][nn] = (gn < n && gk < n) ? B[gn + gk * ld] : 0.0;
+            for (int t = 0; t < 8; ++t) {
+                const int e = tid + t * SG_THREADS;
+                const int mm = e & 127, kk = e >> 7;
+                const int gk = k0 + kk;
+                const int gm = m0 + mm, gn = n0 + mm;
+                const bool oka = gm < n && gk < n, okb = gn < n && gk < n;
+                cp_async8(&As[buf][kk][mm], oka ? A + gm + gk * ld : A, oka ? 8 : 0);
+                cp_async8(&Bs[buf][kk][mm], okb ? B + gn + gk * ld : B, okb ? 8 : 0);
+            }
         }
     };
 
     const int nk = (n + SG_K - 1) / SG_K;
-    load_tiles(0, 0);
-    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < SG_STAGES - 1; ++s) {
+        if (s < nk) load_tiles(s, s * SG_K);
+        cp_async_commit();
+    }
     for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) load_tiles(buf ^ 1, (kt + 1) * SG_K);
+        const int buf = kt % SG_STAGES;
+        cp_async_wait<SG_STAGES - 2>();        // tile kt has landed (this thread's copies) ...
+        __syncthreads();                       // ... and everybody's; everybody is also done with tile kt-1's buffer
+        if (kt + SG_STAGES - 1 < nk) load_tiles((kt + SG_STAGES - 1) % SG_STAGES, (kt + SG_STAGES - 1) * SG_K);
+        cp_async_commit();
 #pragma unroll
         for (int kk = 0; kk < SG_K; kk += 4) {
             double a[4], b[8];
@@ -128,8 +199,8 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
     const double* __restrict__ D = Dp ? Dp + d.off : nullptr;
     double rsum = 0.0;
 #pragma unroll
@@ -144,8 +215,8 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
                 // the iterates must stay EXACTLY symmetric (B is read through its transpose), an
                 // antisymmetric rounding residue of 1e-16 otherwise grows to 1e-9 over the iteration
                 if (gm < n && gn < n && gm >= gn) {
-                    if (mode == 1) {
-                        const double t = acc[i][j][h] - (gm == gn ? 1.0 : 0.0);
+                    if (mode == 1 || mode == 3) {
+                        const double t = acc[i][j][h] - ((gm == gn && mode == 1) ? 1.0 : 0.0);
                         rsum = fma(gm != gn ? 2.0 * t : t, t, rsum);
                     }
                     double v = alpha * acc[i][j][h];
@@ -155,10 +226,10 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
                     if (gm != gn) C[gn + gm * ld] = v;
                 }
             }
-    if (mode == 1) {
+    if (mode == 1 || mode == 3) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-        if (lane == 0) atomicAdd(res_cur + blockIdx.y * res_stride, rsum);
+        if (lane == 0) atomicAdd(res + st.k, rsum);
     }
 }
 
@@ -223,8 +294,20 @@ __global__ void dense_store_kernel(const DenseDesc* __restrict__ desc, const dou
     }
 }
 
-static constexpr int kMaxNsSteps = 60;
-static constexpr double kNsTolSq = 1e-14;   // freeze once ||X^2 - I||_F^2 < 1e-14 (the step after is ~1e-28)
+static constexpr int kMaxNsSteps = 40;
+static constexpr double kNsTolSq = 1e-10;   // freeze once ||X^2 - I||_F^2 < 1e-10 (cubic: the step after is ~1e-30)
+// minimax degree-5 sign polynomials a x + b x^3 + c x^5 on [l_k, 1]  (scripts/sign_poly_table.py, l_0 = 1e-4)
+static constexpr int kSignTable = 7;
+static const double kSignPoly[kSignTable][3] = {
+    {4.2567538552083883, -12.637529108386531, 9.3807751804785546},   // [1.000e-04, 1] -> [0.000426, 1]
+    {4.2554599297572135, -12.626635057799284, 9.3711750746066897},   // [4.257e-04, 1] -> [0.001811, 1]
+    {4.249950912774862, -12.580323192655207, 9.3303722673722636},    // [1.811e-03, 1] -> [0.007698, 1]
+    {4.226491089776534, -12.384384556067777, 9.1578934252368036},    // [7.698e-03, 1] -> [0.032531, 1]
+    {4.1267873247419073, -11.574501430286471, 8.4477140393475434},   // [3.253e-02, 1] -> [0.133848, 1]
+    {3.7225306718083893, -8.6538466523498734, 5.9313159658509376},   // [1.338e-01, 1] -> [0.477758, 1]
+    {2.658148855151357, -3.3824715696999976, 1.7243227088946445},    // [4.778e-01, 1] -> [0.944015, 1]
+};
+static const double kNs5[3] = {15.0 / 8.0, -10.0 / 8.0, 3.0 / 8.0};
 
 struct DensePart {
     int device = -1;
@@ -262,7 +345,7 @@ cuadmm::DensePart* dense_part_create(int device, const std::vector<int32_t>& blk
     D->A.alloc(off); D->X.alloc(off); D->Y.alloc(off); D->Z.alloc(off);
     D->fro2.alloc((int64_t)which.size());
     D->res.alloc((int64_t)which.size() * (kMaxNsSteps + 1));
-    D->smem = sizeof(double) * 2 * SG_K * ((SG_M + SG_PAD) + (SG_N + SG_PAD));
+    D->smem = SG_SMEM;
     CUADMM_CUDA(cudaFuncSetAttribute((const void*)sym_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem));
     return D.release();
 }
@@ -281,26 +364,29 @@ int dense_part_project(cuadmm::DensePart* D, const double* Xb, double* Xproj, cu
     launches += 2;
     const int T = (D->nmax + SG_M - 1) / SG_M;
     dim3 gg(T * (T + 1) / 2, nb);
-    double* X = D->X.p; double* Xn = D->Z.p;
+    double* X = D->X.p; double* Y = D->Y.p; double* Z = D->Z.p;
     const int rs = kMaxNsSteps + 1;
-    // res[.., 0] = +inf-like (never frozen before the first step)
     CUADMM_CUDA(cudaMemsetAsync(D->res.p, 0, sizeof(double) * (size_t)nb * rs, st));
     for (int k = 0; k < kMaxNsSteps; ++k) {
-        // Y = 1.5 I - 0.5 X X (+ residual of step k) ;  X' = X Y   (frozen blocks: copy)
-        const double* rprev = (k == 0) ? nullptr : D->res.p + (k - 1);
-        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, X, D->Y.p, nullptr, -0.5, 1.5, 0.0, done_flag,
-                                                          1, rprev, D->res.p + k, rs, kNsTolSq);
-        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, D->Y.p, Xn, nullptr, 1.0, 0.0, 0.0, done_flag,
-                                                          2, rprev, nullptr, rs, kNsTolSq);
-        std::swap(X, Xn);
-        launches += 2;
+        const double* co = k < kSignTable ? kSignPoly[k] : kNs5;
+        const int s0 = (k == 0);
+        // Y = X X (+ residual of X_k; step 0: ||X_0^2||_F^2, the scale) ; Z = c Y Y + b Y ; Y = X Z + a X ; swap(X, Y)
+        SignStep g1{s0 ? 3 : 1, k, 0, 0, kSignTable + 1}, g2{2, k, s0 ? 4 : 0, s0 ? 2 : 0, kSignTable + 1},
+                 g3{4, k, s0 ? 1 : 0, s0 ? 1 : 0, kSignTable + 1};
+        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, X, Y, nullptr, 1.0, 0.0, 0.0, done_flag, g1, D->res.p, rs, kNsTolSq);
+        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, Y, Y, Z, Y, co[2], 0.0, co[1], done_flag, g2, D->res.p, rs, kNsTolSq);
+        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, Z, Y, X, 1.0, 0.0, co[0], done_flag, g3, D->res.p, rs, kNsTolSq);
+        std::swap(X, Y);
+        launches += 3;
     }
     // P = (U A + A) / 2 with U = sign(A) in X
-    sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, D->A.p, D->Y.p, D->A.p, 0.5, 0.0, 0.5, done_flag,
-                                                      0, nullptr, nullptr, rs, 0.0);
+    SignStep plain{0, 0, 0, 0, 0};
+    sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, D->A.p, Y, D->A.p, 0.5, 0.0, 0.5, done_flag,
+                                                      plain, nullptr, rs, 0.0);
+    double* Pout = Y;
     ProjEpilogue e;
     if (epi) e = *epi; else { e.X = nullptr; e.Rd1 = nullptr; e.Cd = nullptr; e.S = nullptr; e.SmC = nullptr; e.sig_ptr = nullptr; }
-    dense_store_kernel<<<gl, 256, 0, st>>>(D->d_desc.p, D->Y.p, Xproj, e, done_flag);
+    dense_store_kernel<<<gl, 256, 0, st>>>(D->d_desc.p, Pout, Xproj, e, done_flag);
     launches += 2;
     CUADMM_CUDA(cudaGetLastError());
     return launches;
@@ -315,11 +401,12 @@ extern "C" int cuadmm_debug_sym_gemm(int n, const double* hA, const double* hB, 
         DenseDesc d; d.off = 0; d.svec_off = 0; d.n = n; d.pad = 0;
         DevBuf<DenseDesc> dd(1);
         CUADMM_CUDA(cudaMemcpy(dd.p, &d, sizeof d, cudaMemcpyHostToDevice));
-        const size_t smem = sizeof(double) * 2 * SG_K * ((SG_M + SG_PAD) + (SG_N + SG_PAD));
+        const size_t smem = SG_SMEM;
         CUADMM_CUDA(cudaFuncSetAttribute((const void*)sym_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int T = (n + SG_M - 1) / SG_M;
+        SignStep plain{0, 0, 0, 0, 0};
         sym_gemm_kernel<<<dim3(T * (T + 1) / 2, 1), SG_THREADS, smem>>>(dd.p, A.p, B.p, C.p, nullptr, alpha, dshift, 0.0, nullptr,
-                                                                        0, nullptr, nullptr, 1, 0.0);
+                                                                        plain, nullptr, 1, 0.0);
         CUADMM_CUDA(cudaGetLastError());
         C.download(hC, nn);
         CUADMM_CUDA(cudaDeviceSynchronize());

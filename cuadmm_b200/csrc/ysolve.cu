@@ -369,19 +369,38 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
                                                         double* out, const int32_t* __restrict__ tile_ptr,
                                                         const int32_t* __restrict__ tile_col, double* out_scatter,
                                                         const int32_t* __restrict__ out_perm, int64_t perm_base,
-                                                        const int* __restrict__ done_flag) {
+                                                        const int* __restrict__ done_flag, int longest_last) {
     if (done_flag && *done_flag) return;
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // the CTAs with the longest rows go first (lower-triangular storage: the last rows), so the grid's tail
+    // wave is made of short rows
+    const int64_t cta = longest_last ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int64_t row = cta * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= r) return;
     const double* Ti = T + row * r;
     const int I = (int)(row >> 6);
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
+    const bool vec = (r & 1) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0;   // rows 16-byte aligned (tile columns are multiples of 64)
+    const bool in_al = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     for (int t = tile_ptr[I]; t < tile_ptr[I + 1]; ++t) {      // runs of consecutive non-empty tiles: [first, last) columns
+        const int64_t j0 = tile_col[2 * t];
         const int64_t j1 = min((int64_t)tile_col[2 * t + 1], r);
+        if (vec) {
+            const int64_t jv = j0 + ((j1 - j0) & ~(int64_t)1);
 #pragma unroll 4
-        for (int64_t j = (int64_t)tile_col[2 * t] + lane; j < j1; j += 32) acc = fma(Ti[j], in[j], acc);
+            for (int64_t j = j0 + 2 * lane; j < jv; j += 64) {
+                const double2 a = __ldcs(reinterpret_cast<const double2*>(Ti + j));   // streamed once: evict first
+                const double2 b = in_al ? *reinterpret_cast<const double2*>(in + j) : make_double2(in[j], in[j + 1]);
+                acc0 = fma(a.x, b.x, acc0);
+                acc1 = fma(a.y, b.y, acc1);
+            }
+            if (lane == 0 && jv < j1) acc0 = fma(Ti[jv], in[jv], acc0);
+        } else {
+#pragma unroll 4
+            for (int64_t j = j0 + lane; j < j1; j += 32) acc0 = fma(Ti[j], in[j], acc0);
+        }
     }
+    double acc = acc0 + acc1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -1079,9 +1098,9 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
         const int blocks = (int)((n_tail + 7) / 8);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
         tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tail_tmp.p, tail_tptr.p, tail_tcol.p,
-                                                 nullptr, nullptr, 0, done_flag);
+                                                 nullptr, nullptr, 0, done_flag, 1);
         tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tail_tmp.p, x.p + n_lead, tail_tptr_t.p, tail_tcol_t.p,
-                                                 d_y_, perm.p, n_lead, done_flag);
+                                                 d_y_, perm.p, n_lead, done_flag, 0);
         CUADMM_CUDA(cudaGetLastError());
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y

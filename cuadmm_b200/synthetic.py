@@ -23,6 +23,13 @@ def c2b_blocks(nblk=2000, lo=6, hi=60, seed=0):
     return np.random.default_rng(seed).integers(lo, hi + 1, nblk).astype(np.int32)
 
 
+def c4_blocks(seed=0, counts=((10, 6000), (50, 3000), (200, 900), (800, 100))):
+    """BASELINE.json configs[3]: 10,000 blocks of mixed sizes in shuffled order"""
+    blk = np.concatenate([np.full(c, n, np.int32) for n, c in counts])
+    np.random.default_rng(seed).shuffle(blk)
+    return blk
+
+
 def random_svec(blk, seed=0):
     """random symmetric blocks (G + G^T)/2, G ~ N(0,1), eigenvalues straddling 0"""
     rng = np.random.default_rng(seed)
@@ -64,6 +71,46 @@ def chain_sdp(blk, m, seed=0, extra_frac=0.1):
     hb = np.repeat(home, k)
     nxt = np.minimum(hb + (rng.random(tot) < 0.35), nb - 1)
     ent = off[nxt] + (rng.random(tot) * (off[nxt + 1] - off[nxt])).astype(np.int64)
+    val = rng.standard_normal(tot)
+    A = sp.csr_matrix((val, (con, ent)), shape=(m, vec_len))
+    A.sum_duplicates(); A.sort_indices()
+    b = A @ xstar
+    ystar = rng.standard_normal(m)
+    C = sstar + A.T @ ystar
+    nzb = np.nonzero(b)[0]; nzc = np.nonzero(C)[0]
+    return dict(blk=blk, vec_len=vec_len, con_num=m, col_ptrs=A.indptr.astype(np.int32),
+                row_ids=A.indices.astype(np.int32), vals=A.data.astype(np.float64),
+                b_idx=nzb.astype(np.int32), b_val=b[nzb], C_idx=nzc.astype(np.int32), C_val=C[nzc],
+                xstar=xstar, pstar=float(C @ xstar))
+
+
+def random_sdp(blk, m, seed=0, mean_extra=4.0):
+    """BASELINE.json configs[3] as defined in SURVEY 8d: m constraints, each with k ~ 1 + Poisson(mean_extra)
+    non-zeros at uniformly random svec positions of at most 2 blocks (the two blocks drawn with probability
+    proportional to their svec length, i.e. positions are uniform over the svec vector), values N(0,1);
+    b = A svec(X*) for a random PSD X*, C = svec(S*) + A^T y* with X* S* = 0 (optimum known)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    blk = np.asarray(blk, np.int32)
+    nb = len(blk)
+    off = svec_offsets(blk)
+    vec_len = int(off[-1])
+    xs, ss = [], []
+    for n in blk:
+        n = int(n)
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        r = max(1, n // 3)
+        lam = np.zeros(n); lam[:r] = rng.uniform(0.5, 2.0, r)
+        mu = np.zeros(n); mu[r:] = rng.uniform(0.5, 2.0, n - r)
+        xs.append(_svec((Q * lam) @ Q.T)); ss.append(_svec((Q * mu) @ Q.T))
+    xstar, sstar = np.concatenate(xs), np.concatenate(ss)
+    w = np.diff(off).astype(float)
+    two = rng.choice(nb, size=(m, 2), p=w / w.sum())
+    k = 1 + rng.poisson(mean_extra, m)
+    tot = int(k.sum())
+    con = np.repeat(np.arange(m), k)
+    bsel = two[con, (rng.random(tot) < 0.5).astype(np.int64)]
+    ent = off[bsel] + (rng.random(tot) * (off[bsel + 1] - off[bsel])).astype(np.int64)
     val = rng.standard_normal(tot)
     A = sp.csr_matrix((val, (con, ent)), shape=(m, vec_len))
     A.sum_duplicates(); A.sort_indices()
