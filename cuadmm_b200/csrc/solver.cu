@@ -267,7 +267,9 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
             comm->init(rank, world, nccl_id, device);
             red_buf.alloc(con_num + 2);
             d_loc2glob.upload(shard.loc2glob);
-            use_graphs = false;                      // NCCL calls are enqueued directly
+            // NCCL collectives are capturable; off by default until measured on more than 2 GPUs (CUADMM_DIST_GRAPH=1)
+            const char* dg = getenv("CUADMM_DIST_GRAPH");
+            if (!(dg && atoi(dg) != 0)) use_graphs = false;
         }
     }
     // ---- A: normalise the constraints (get_normA, src/solver.cu:79-80), same arithmetic
@@ -351,7 +353,7 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
     }
     up(X, hX); up(S, hS); up(y, hy); up(Rp, hRp); up(SmC, hSmC); up(Cd, hC); up(bd, hb); up(normA, h_normA);
     Rd1.alloc(std::max<int64_t>(nloc, 1)); Rd.alloc(std::max<int64_t>(nloc, 1)); Xb.alloc(std::max<int64_t>(nloc, 1));
-    Xproj.alloc(std::max<int64_t>(nloc, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1));
+    Xproj.alloc(std::max<int64_t>(nloc, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1)); asmc.alloc(std::max<int64_t>(con_num, 1)); asmc_valid = false;
     Rd1.zero(stream); Rd.zero(stream);
     nA_blocks = spmv_grid(*A); nAt_blocks = spmv_grid(*At); nE_blocks = ew_grid(std::max(nloc, con_num), device);
     partial.alloc(2 * (int64_t)(std::max(nAt_blocks, nE_blocks) + std::max(nA_blocks, nE_blocks)) + 4);
@@ -395,20 +397,19 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         (void)k;
     };
     const int gm_ = ew_grid(con_num, device);
-    // K1  (multi-GPU: partial -A_g (S-C)_g, all-reduce, then rhsy = Rp/sig + sum)
-    auto k1 = [&]() {
-        if (world == 1) {
-            e = SpmvEpilogue(); e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
-            spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
-        } else {
+    // K1: rhsy = Rp/sig - A(S-C).  The product asmc = -A(S-C) is kept: in an sGS iteration K5 computes it for
+    // the NEW S, which is exactly what K1 of the next iteration needs (S does not change in between), so that
+    // K1 is then only the vector update — one SpMV (and, multi-GPU, one all-reduce) less per sGS iteration than
+    // the reference's loop (src/solver.cu:478-482 recomputes it).  Multi-GPU: partial -A_g (S-C)_g, all-reduce.
+    auto k1 = [&](bool cached) {
+        if (!cached) {
             e = SpmvEpilogue();
-            spmv_launch(*A, -1.0, SmC.p, 0.0, red_buf.p, e, stream);
-            comm->allreduce_sum(red_buf.p, con_num, stream);
-            rhsy_kernel<<<gm_, 256, 0, stream>>>(con_num, Rp.p, red_buf.p, rhsy.p, st.p);
-            launches += 3;
+            spmv_launch(*A, -1.0, SmC.p, 0.0, asmc.p, e, stream); ++launches;
+            if (world > 1) { comm->allreduce_sum(asmc.p, con_num, stream); ++launches; }
         }
+        rhsy_kernel<<<gm_, 256, 0, stream>>>(con_num, Rp.p, asmc.p, rhsy.p, st.p); ++launches;
     };
-    k1();
+    k1(asmc_valid);
     // K2
     mark(0);
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
@@ -433,7 +434,7 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
     int n_rd = 0;
     if (iter < switch_admm) {
         // K5-K7: the sGS second half-step
-        k1();
+        k1(false);
         mark(4);
         ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
         mark(5);
@@ -468,6 +469,7 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, red_buf.p + con_num, 1, part_rp, nE_blocks, hist.p, hist_cap);
         launches += 5;
     }
+    asmc_valid = iter < switch_admm;     // K5 ran: asmc holds -A(S-C) of the S this iteration ends with
     CUADMM_CUDA(cudaGetLastError());
 }
 
@@ -475,8 +477,10 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
 // except at iter == switch_admm, which is enqueued directly).  Launch-bound problems (ros_2000: ~15
 // kernels of a few microseconds each) otherwise spend more time in the driver than on the GPU.
 void cuadmm_solver::launch_iteration(int iter, int switch_admm, bool prof) {
-    if (prof || !use_graphs || iter == switch_admm) { enqueue_iteration(iter, switch_admm, prof); return; }
     const bool sgs = iter < switch_admm;
+    // the sGS graph is the steady-state sequence (K1 from the cached product), the ADMM graph recomputes it;
+    // an iteration that starts in the other cache state is enqueued directly
+    if (prof || !use_graphs || iter == switch_admm || sgs != asmc_valid) { enqueue_iteration(iter, switch_admm, prof); return; }
     cudaGraphExec_t& exec = sgs ? graph_sgs : graph_admm;
     int64_t& nl = sgs ? graph_launches_sgs : graph_launches_admm;
     if (!exec) {
@@ -498,22 +502,18 @@ void cuadmm_solver::launch_iteration(int iter, int switch_admm, bool prof) {
     }
     CUADMM_CUDA(cudaGraphLaunch(exec, stream));
     launches += nl;
+    asmc_valid = sgs;
 }
 
 // what the reference still executes at the top of the iteration in which it breaks
 // (step 1 and step 2a, src/solver.cu:478-528): y is overwritten by the next half-step.
 void cuadmm_solver::enqueue_half_step() {
-    const double* scal = &st.p->sig;
     SpmvEpilogue e;
-    if (world == 1) {
-        e.mode = 1; e.aux1 = Rp.p; e.scal = scal;
-        spmv_launch(*A, 1.0, SmC.p, 0.0, rhsy.p, e, stream); ++launches;
-    } else {
-        spmv_launch(*A, -1.0, SmC.p, 0.0, red_buf.p, e, stream);
-        comm->allreduce_sum(red_buf.p, con_num, stream);
-        rhsy_kernel<<<ew_grid(con_num, device), 256, 0, stream>>>(con_num, Rp.p, red_buf.p, rhsy.p, st.p);
-        launches += 3;
+    if (!asmc_valid) {
+        spmv_launch(*A, -1.0, SmC.p, 0.0, asmc.p, e, stream); ++launches;
+        if (world > 1) { comm->allreduce_sum(asmc.p, con_num, stream); ++launches; }
     }
+    rhsy_kernel<<<ew_grid(con_num, device), 256, 0, stream>>>(con_num, Rp.p, asmc.p, rhsy.p, st.p); ++launches;
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
 }
 
@@ -596,6 +596,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
         if (graph_admm) { cudaGraphExecDestroy(graph_admm); graph_admm = nullptr; }
     }
     info_iter_num = 0;
+    asmc_valid = false;                  // X, y, S may have been replaced / rescaled since the last call
 
     // state for this call
     CUADMM_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
@@ -790,6 +791,7 @@ int cuadmm_solver_set_XyS(cuadmm_solver_t* s, const double* h_X, const double* h
         if (h_X) s->X.upload(h_X, s->nloc, s->stream);
         if (h_y) s->y.upload(h_y, s->con_num, s->stream);
         if (h_S) s->S.upload(h_S, s->nloc, s->stream);
+        s->asmc_valid = false;
         CUADMM_CUDA(cudaStreamSynchronize(s->stream));
         CUADMM_CUDA(cudaMemcpyAsync(&s->st.p->sig, &sig, sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUADMM_CUDA(cudaStreamSynchronize(s->stream));

@@ -85,5 +85,7 @@ struct cuadmm_solver {
     cudaGraphExec_t graph_sgs = nullptr, graph_admm = nullptr;
     int64_t graph_launches_sgs = 0, graph_launches_admm = 0;
     bool use_graphs = true;
+    cuadmm::DevBuf<double> asmc;             // -A (S-C) (all-reduced when sharded), reused by the next iteration's K1
+    bool asmc_valid = false;
     void launch_iteration(int iter, int switch_admm, bool prof);
 };

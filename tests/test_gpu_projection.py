@@ -251,3 +251,35 @@ def test_warm_start_matches_cold_and_oracle():
     ow, _, _ = warm.project_eig_host(x)
     ref = onp.project_svec(blk, x)
     assert np.abs(ow - ref).max() <= 2e-13 * np.abs(ref).max()
+
+
+def _identities(blk, x):
+    """size-independent properties of Pi_+: idempotence, Moreau decomposition x = Pi(x) - Pi(-x), orthogonality"""
+    p = cu.Plan(np.asarray(blk, np.int32))
+    a = p.project_host(x)
+    b = p.project_host(-x)
+    aa = p.project_host(a)
+    nx = np.linalg.norm(x)
+    assert np.linalg.norm(aa - a) <= 1e-11 * nx
+    assert np.linalg.norm(a - b - x) <= 1e-12 * nx
+    assert abs(a @ b) <= 1e-12 * nx * nx
+    return a
+
+
+def test_c4_block_mix_identities_and_oracle_sample():
+    # BASELINE configs[3] block mix {10, 50, 200, 800} at 1/20 of the block count, shuffled like the full case
+    blk = np.concatenate([np.full(300, 10), np.full(150, 50), np.full(45, 200), np.full(5, 800)]).astype(np.int32)
+    np.random.default_rng(0).shuffle(blk)
+    x = random_svec(blk, seed=4)
+    a = _identities(blk, x)
+    off = onp.svec_offsets(blk)
+    picks = [int(np.flatnonzero(blk == n)[0]) for n in (10, 50, 200, 800)] + [int(np.flatnonzero(blk == 200)[-1])]
+    for k in picks:
+        ref = onp.project_svec(blk[k:k + 1], x[off[k]:off[k + 1]])
+        assert np.linalg.norm(a[off[k]:off[k + 1]] - ref) <= X_TOL * np.linalg.norm(ref), (k, blk[k])
+
+
+def test_c3_single_block_n4000_identities():
+    # BASELINE configs[2]: one dense block n = 4000 (a CPU eigendecomposition of this size is left to the bench baseline)
+    blk = np.array([4000], np.int32)
+    _identities(blk, random_svec(blk, seed=6))
