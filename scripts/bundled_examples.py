@@ -5,6 +5,8 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from util_problems import load_fixture, make_solver
+SWITCH = int(os.environ.get("CUADMM_EX_SWITCH", "5000"))      # src/main.cu:39 passes 5000; solver.h:242 defaults to 11000
+CAP = int(os.environ.get("CUADMM_EX_CAP", "15000"))
 REF = {"pusht_n10": ("sGS-cuADMM.log", 30.3), "ros_2000": ("sGS-cuADMM.log", 1.3), "rose13": ("rose13.log", 3.5)}
 out = []
 for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "c2b"]:
@@ -19,15 +21,15 @@ for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "c2b"]:
     r = s.run_iterations(300, sgs=True)
     row = {"example": name, "nblk": int(len(P["blk"])), "vec_len": int(P["vec_len"]), "con_num": int(P["con_num"]),
            "ms_per_iter_sgs": r["total_ms"] / 300, "init_s": t_init,
-           "reference_log_ms_per_iter": REF.get(name, (None, None))[1], "reference_log": REF.get(name, (None, None))[0]}
+           "switch_admm": SWITCH, "reference_log_ms_per_iter": REF.get(name, (None, None))[1], "reference_log": REF.get(name, (None, None))[0]}
     # time to the reference's own stop tolerance (src/main.cu:39: 1e-3) and to 1e-6, fresh solver
     for tol, key in ((1e-3, "to_1e-3"), (1e-6, "to_1e-6")):
         # rose13 needs 60,000 iterations in the reference's log: ms/iteration only; bounded GPU time otherwise
         if name == "rose13" or (name == "c2b") != (tol == 1e-6):
             continue
         s2 = make_solver(P, verbose=False)
-        cap = 15000
-        t = time.time(); s2.solve(cap, tol, 0, 50, 100, 5000); dt = time.time() - t
+        cap = CAP
+        t = time.time(); s2.solve(cap, tol, 0, 50, 100, SWITCH); dt = time.time() - t
         kkt = max(s2.history("errRp")[-1], s2.history("errRd")[-1], s2.history("relgap")[-1])
         row[key] = {"iters": int(s2.info_iter_num), "seconds": dt, "reached": bool(kkt < tol), "max_kkt": float(kkt)}
         if "pstar" in P:
@@ -35,4 +37,4 @@ for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "c2b"]:
     print(json.dumps(row), flush=True)
     out.append(row)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bundled_examples.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bundled_examples_switch%d.json" % SWITCH), "w"), indent=1)
