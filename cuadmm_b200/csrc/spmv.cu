@@ -10,6 +10,7 @@
 // (value + int32 column), coalesced across the lanes of a group.
 #include "spmv.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace cuadmm {
 
@@ -221,13 +222,40 @@ cuadmm_spmv_s* spmv_create(int64_t rows, int64_t cols, int64_t nnz, const int32_
     const double mean = short_rows ? (double)short_nnz / (double)short_rows : 1.0;
     int G = 1;
     while (G < 32 && (double)G < mean) G <<= 1;   // smallest power of two >= mean row length
+    // measured on B200 (profiles/spmv_probe_r01.json, the bench operator, 2.2 and 1.5 entries per row): one lane per
+    // row beats 2 or 4 lanes (12.4 us vs 20.4 us for A) — with rows this short the sub-warp reduction and the idle
+    // lanes of the epilogue cost more than the uncoalesced value/column loads.  Only for matrices large enough to be
+    // throughput-bound (several rows per resident thread); small ones (PushT: 28k rows) are latency-bound and keep
+    // the lanes of a row working in parallel (measured: 0.405 vs 0.446 ms per iteration)
+    if (mean <= 4.0 && rows >= 262144) G = 1;
+    if (const char* e = getenv("CUADMM_SPMV_G")) {   // tuning override: 1, 2, 4, ... 32
+        const int g = atoi(e);
+        if (g >= 1 && g <= 32 && (g & (g - 1)) == 0) G = g;
+    }
     A->group = G;
     A->aux.n_long = (int)longs.size();
     if (!longs.empty()) { A->aux.long_rows.upload(longs); }
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
     const int64_t need = (rows * G + kThreads - 1) / kThreads;
-    A->aux.main_blocks = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)sm * 8);
+    // one resident wave: the grid is capped at the CTAs per SM the kernel can keep resident (5 at 48 registers);
+    // 8 per SM made 1.6 waves and cost 20-25 % (same probe).  CUADMM_SPMV_CAP overrides.
+    int cap = 5;
+    {
+        int occ = 0;
+        cudaError_t rc = cudaErrorUnknown;
+        switch (G) {
+            case 1: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<1>, kThreads, 0); break;
+            case 2: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<2>, kThreads, 0); break;
+            case 4: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<4>, kThreads, 0); break;
+            case 8: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<8>, kThreads, 0); break;
+            case 16: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<16>, kThreads, 0); break;
+            default: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<32>, kThreads, 0); break;
+        }
+        if (rc == cudaSuccess && occ >= 1) cap = occ; else cudaGetLastError();
+    }
+    if (const char* e = getenv("CUADMM_SPMV_CAP")) { const int c = atoi(e); if (c >= 1 && c <= 32) cap = c; }
+    A->aux.main_blocks = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)sm * cap);
     A->aux.long_blocks = longs.empty() ? 0 : (int)std::min<int64_t>(((int64_t)longs.size() + 7) / 8, (int64_t)sm);
     CUADMM_CUDA(cudaStreamSynchronize(0));
     return A.release();
