@@ -7,5 +7,5 @@ fails loudly, and compute entry points fail with CUADMM_ENODEVICE when no GPU is
 """
 from .capi import (  # noqa: F401
     lib, LIB_PATH, CuadmmError, Plan, SpMV, YSolve, Solver, Problem, device_count, version,
-    normA_host, csc_to_csr_host, Shard, nccl_unique_id,
+    normA_host, csc_to_csr_host, Shard, nccl_unique_id, unique_id,
 )

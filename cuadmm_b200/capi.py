@@ -321,6 +321,8 @@ _maybe("cuadmm_solver_launches", C.c_int64, vp)
 _maybe("cuadmm_solver_run_iterations", C.c_int, vp, C.c_int, C.c_int, C.c_int, c_f64p)
 _maybe("cuadmm_solver_ysolve_stats", C.c_int, vp, c_i64p)
 _maybe("cuadmm_nccl_unique_id", C.c_int, C.c_char_p)
+_maybe("cuadmm_unique_id", C.c_int, C.c_char_p)
+_maybe("cuadmm_solver_set_device", C.c_int, vp, C.c_int)
 _maybe("cuadmm_solver_set_distributed", C.c_int, vp, C.c_int, C.c_int, C.c_char_p)
 _maybe("cuadmm_shard_create", C.c_int, c_i32p, C.c_int64, C.c_int, C.c_int, C.POINTER(vp))
 _maybe("cuadmm_shard_destroy", None, vp)
@@ -333,6 +335,13 @@ _maybe("cuadmm_solver_init_from_problem", C.c_int, vp, vp, C.c_int, C.c_int, C.c
 def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _check(lib.cuadmm_nccl_unique_id(buf))
+    return buf.raw
+
+
+def unique_id():
+    """128 random bytes: job id of the peer-memory transport (rank 0 creates it, the launcher broadcasts it)"""
+    buf = C.create_string_buffer(128)
+    _check(lib.cuadmm_unique_id(buf))
     return buf.raw
 
 
@@ -432,6 +441,9 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+    def set_device(self, device):
+        _check(lib.cuadmm_solver_set_device(self.h, int(device)))
 
     def set_distributed(self, rank, world, nccl_id):
         """one process per GPU: call before init with the id rank 0 got from nccl_unique_id()"""

@@ -49,14 +49,16 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     int64_t n = 0;
+    bool owned = true;      // false: a view of memory owned elsewhere (the peer arena)
     DevBuf() {}
     explicit DevBuf(int64_t n_) { alloc(n_); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
+    void adopt(T* ptr, int64_t n_) { release(); p = ptr; n = n_; owned = false; }
     void alloc(int64_t n_) {
         release();
         n = n_;

@@ -54,9 +54,9 @@ void NcclComm::init(int rank_, int world_, const char id[128], int device) {
     check(api().init(&comm, world, uid, rank), "ncclCommInitRank");
 }
 
-void NcclComm::allreduce_sum(double* buf, int64_t count, cudaStream_t stream) {
+void NcclComm::allreduce_sum(const double* send, double* recv, int64_t count, cudaStream_t stream) {
     // ncclFloat64 = 8, ncclSum = 0
-    check(api().allreduce(buf, buf, (size_t)count, 8, 0, comm, stream), "ncclAllReduce");
+    check(api().allreduce(send, recv, (size_t)count, 8, 0, comm, stream), "ncclAllReduce");
 }
 
 NcclComm::~NcclComm() {

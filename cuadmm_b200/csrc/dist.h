@@ -10,8 +10,8 @@ struct NcclComm {
     int rank = 0, world = 1;
     ~NcclComm();
     void init(int rank, int world, const char id[128], int device);
-    // in-place sum all-reduce of `count` doubles on `stream`
-    void allreduce_sum(double* buf, int64_t count, cudaStream_t stream);
+    // sum all-reduce of `count` doubles on `stream` (send == recv: in place)
+    void allreduce_sum(const double* send, double* recv, int64_t count, cudaStream_t stream);
 };
 
 void nccl_unique_id(char out[128]);

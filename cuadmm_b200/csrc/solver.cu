@@ -238,7 +238,11 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
         cudaGetLastError();
         throw Error(CUADMM_ENODEVICE, "no CUDA device available; the solver has no CPU fallback");
     }
-    if (const char* e = getenv("CUADMM_DEVICE")) device = atoi(e);
+    // device: cuadmm_solver_set_device, else CUADMM_DEVICE, else the calling thread's current device
+    if (!device_set) {
+        if (const char* e = getenv("CUADMM_DEVICE")) device = atoi(e);
+        else { int cur = 0; if (cudaGetDevice(&cur) == cudaSuccess) device = cur; else cudaGetLastError(); }
+    }
     if (const char* e = getenv("CUADMM_NO_GRAPH")) use_graphs = atoi(e) == 0;
     CUADMM_REQUIRE(device >= 0 && device < cnt, "device index out of range");
     CUADMM_CUDA(cudaSetDevice(device));
@@ -263,11 +267,9 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
         plan->device = device;
         plan->build_device();
         if (world > 1) {
-            comm.reset(new NcclComm());
-            comm->init(rank, world, nccl_id, device);
-            red_buf.alloc(con_num + 2);
             d_loc2glob.upload(shard.loc2glob);
-            // the NCCL all-reduces are captured into the iteration graph with the kernels (measured on 2 GPUs: 672 ->
+            if (const char* c = getenv("CUADMM_COMM")) use_peer = strcmp(c, "nccl") != 0;
+            // the collectives are captured into the iteration graph with the kernels (measured on 2 GPUs: 672 ->
             // 857 iter/s on the bench workload; without it the host cannot enqueue ~40 launches per 1.2 ms iteration
             // fast enough); CUADMM_DIST_GRAPH=0 enqueues them directly
             if (const char* dg = getenv("CUADMM_DIST_GRAPH")) { if (atoi(dg) == 0) use_graphs = false; }
@@ -304,6 +306,34 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
     }
     // ---- A A^T factorisation (src/solver.cu:91-110), eps = 1e-15
     ys = ysolve_create(con_num, vec_len, At_nnz, At_col_ptrs, At_row_ids, vals.data(), 1e-15, device);
+    if (world > 1) {
+        if (use_peer) {
+            // peer arena: staging for the slice reduction, the replicated m-vectors the peers store into (asmc, Rp, y,
+            // the y-solve's x and dense-tail vector) and a full-length svec vector for get_X / get_S
+            CUADMM_REQUIRE(con_num < (int64_t)0xffffffffll, "sharded solver: con_num exceeds 32 bits");
+            slice = (((con_num + world - 1) / world) + 1) & ~(int64_t)1;
+            const int64_t mm = std::max<int64_t>(con_num, 1);
+            const size_t need = sizeof(double) * (size_t)(world * slice + 4 * mm + std::max<int64_t>(ys->n_tail, 1) + std::max<int64_t>(vec_len, 1)) + 16 * 256;
+            peer.reset(new PeerComm());
+            peer->init(rank, world, nccl_id, device, need);
+            const size_t o_stage = peer->alloc(sizeof(double) * world * slice);
+            const size_t o_asmc = peer->alloc(sizeof(double) * mm), o_Rp = peer->alloc(sizeof(double) * mm), o_y = peer->alloc(sizeof(double) * mm);
+            const size_t o_x = peer->alloc(sizeof(double) * mm), o_tmp = peer->alloc(sizeof(double) * std::max<int64_t>(ys->n_tail, 1));
+            const size_t o_full = peer->alloc(sizeof(double) * std::max<int64_t>(vec_len, 1));
+            stage = peer->local<double>(o_stage);
+            p_stage = peer->ptrs(o_stage); p_asmc = peer->ptrs(o_asmc); p_Rp = peer->ptrs(o_Rp); p_full = peer->ptrs(o_full);
+            asmc.adopt(peer->local<double>(o_asmc), mm); Rp.adopt(peer->local<double>(o_Rp), mm); y.adopt(peer->local<double>(o_y), mm);
+            full_buf.adopt(peer->local<double>(o_full), std::max<int64_t>(vec_len, 1));
+            ys->enable_peer(peer.get(), o_tmp, o_x);
+            cta_part.alloc(2 * (int64_t)peer_reduce_grid(*peer, slice) + 2);
+        } else {
+            comm.reset(new NcclComm());
+            comm->init(rank, world, nccl_id, device);
+            red_buf.alloc(con_num + 2);
+            asmc_part.alloc(std::max<int64_t>(con_num, 1));
+            asmc_part.zero(stream);
+        }
+    }
 
     // ---- b, C, X, y, S and the scaling (src/solver.cu:113-191)
     std::vector<double> hb(con_num, 0.0), hC(vec_len, 0.0), hX(vec_len, 0.0), hy(con_num, 0.0), hS(vec_len, 0.0);
@@ -344,7 +374,10 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
     }
 
     // ---- device vectors
-    auto up = [&](DevBuf<double>& d, const std::vector<double>& h) { d.alloc(std::max<int64_t>((int64_t)h.size(), 1)); d.upload(h.data(), (int64_t)h.size(), stream); };
+    auto up = [&](DevBuf<double>& d, const std::vector<double>& h) {
+        if (d.owned || !d.p) d.alloc(std::max<int64_t>((int64_t)h.size(), 1));     // views of the peer arena are kept
+        d.upload(h.data(), (int64_t)h.size(), stream);
+    };
     if (world > 1) {   // keep only the owned svec ranges of X, S, S-C, C
         std::vector<double> t;
         shard.slice_vec(hX.data(), t); hX.swap(t);
@@ -354,7 +387,7 @@ void cuadmm_solver::init(int /*eig_stream_num_per_gpu*/, int /*cpu_eig_thread_nu
     }
     up(X, hX); up(S, hS); up(y, hy); up(Rp, hRp); up(SmC, hSmC); up(Cd, hC); up(bd, hb); up(normA, h_normA);
     Rd1.alloc(std::max<int64_t>(nloc, 1)); Rd.alloc(std::max<int64_t>(nloc, 1)); Xb.alloc(std::max<int64_t>(nloc, 1));
-    Xproj.alloc(std::max<int64_t>(nloc, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1)); asmc.alloc(std::max<int64_t>(con_num, 1)); asmc_valid = false;
+    Xproj.alloc(std::max<int64_t>(nloc, 1)); rhsy.alloc(std::max<int64_t>(con_num, 1)); if (asmc.owned || !asmc.p) asmc.alloc(std::max<int64_t>(con_num, 1)); asmc_valid = false;
     Rd1.zero(stream); Rd.zero(stream);
     nA_blocks = spmv_grid(*A); nAt_blocks = spmv_grid(*At); nE_blocks = ew_grid(std::max(nloc, con_num), device);
     partial.alloc(2 * (int64_t)(std::max(nAt_blocks, nE_blocks) + std::max(nA_blocks, nE_blocks)) + 4);
@@ -404,9 +437,8 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
     // the reference's loop (src/solver.cu:478-482 recomputes it).  Multi-GPU: partial -A_g (S-C)_g, all-reduce.
     auto k1 = [&](bool cached) {
         if (!cached) {
-            e = SpmvEpilogue();
-            spmv_launch(*A, -1.0, SmC.p, 0.0, asmc.p, e, stream); ++launches;
-            if (world > 1) { comm->allreduce_sum(asmc.p, con_num, stream); ++launches; }
+            if (world == 1) { e = SpmvEpilogue(); spmv_launch(*A, -1.0, SmC.p, 0.0, asmc.p, e, stream); ++launches; }
+            else reduce_partial_A(false, SmC.p, -1.0, nullptr, 0, nullptr);
         }
         rhsy_kernel<<<gm_, 256, 0, stream>>>(con_num, Rp.p, asmc.p, rhsy.p, st.p); ++launches;
     };
@@ -462,13 +494,13 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         // K9
         scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, part_rd, n_rd, part_rp, nA_blocks, hist.p, hist_cap); ++launches;
     } else {
-        e = SpmvEpilogue();
-        spmv_launch(*A, 1.0, X.p, 0.0, red_buf.p, e, stream);
-        fold_partials_kernel<<<1, 256, 0, stream>>>(part_rd, n_rd, red_buf.p + con_num, st.p);
-        comm->allreduce_sum(red_buf.p, con_num + 2, stream);
-        rp_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(con_num, bd.p, red_buf.p, normA.p, y.p, Rp.p, st.p, part_rp);
-        scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, red_buf.p + con_num, 1, part_rp, nE_blocks, hist.p, hist_cap);
-        launches += 5;
+        reduce_partial_A(true, X.p, 1.0, part_rd, n_rd, part_rp);
+        if (use_peer)   // every rank adds the per-rank scalars in rank order: bit-identical state on all ranks
+            scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, peer->local<double>(peer->off_scal_rd), world,
+                                                        peer->local<double>(peer->off_scal_rp), world, hist.p, hist_cap);
+        else
+            scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, red_buf.p + con_num, 1, part_rp, nE_blocks, hist.p, hist_cap);
+        ++launches;
     }
     asmc_valid = iter < switch_admm;     // K5 ran: asmc holds -A(S-C) of the S this iteration ends with
     CUADMM_CUDA(cudaGetLastError());
@@ -506,13 +538,44 @@ void cuadmm_solver::launch_iteration(int iter, int switch_admm, bool prof) {
     asmc_valid = sgs;
 }
 
+// Sharded solver: sum over ranks of the partial products alpha * A[:, I_g] x_g.
+//   for_rp == false:  asmc = sum                                     (K1 / K5)
+//   for_rp == true :  Rp = b - sum, residual scalars for K9          (K8)
+// Peer transport: the SpMV stores every partial row into the staging area of the rank that reduces it (mode 5),
+// peer_reduce_kernel sums its slice, applies the consumer and stores the result into every rank's copy.
+// NCCL transport: SpMV into a local buffer, ncclAllReduce, consumer kernel.
+void cuadmm_solver::reduce_partial_A(bool for_rp, const double* x_local, double alpha, const double* part_rd, int n_rd, double* part_rp) {
+    SpmvEpilogue e;
+    if (use_peer) {
+        e.mode = 5; e.slice = (unsigned)slice; e.rank = rank;
+        for (int q = 0; q < world; ++q) e.push[q] = p_stage.p[q];
+        spmv_launch(*A, alpha, x_local, 0.0, stage, e, stream);
+        peer_reduce_launch(*peer, for_rp ? 1 : 0, con_num, slice, stage, for_rp ? p_Rp : p_asmc, bd.p, normA.p, y.p, part_rd, n_rd,
+                           cta_part.p, &st.p->done, stream);
+        launches += 2;
+        return;
+    }
+    if (!for_rp) {
+        // out of place: a skipped SpMV (device stop flag set) leaves the partial, hence the sum, unchanged
+        spmv_launch(*A, alpha, x_local, 0.0, asmc_part.p, e, stream);
+        comm->allreduce_sum(asmc_part.p, asmc.p, con_num, stream);
+        launches += 2;
+        return;
+    }
+    spmv_launch(*A, alpha, x_local, 0.0, red_buf.p, e, stream);
+    if (part_rd) fold_partials_kernel<<<1, 256, 0, stream>>>(part_rd, n_rd, red_buf.p + con_num, st.p);
+    comm->allreduce_sum(red_buf.p, red_buf.p, con_num + 2, stream);
+    rp_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(con_num, bd.p, red_buf.p, normA.p, y.p, Rp.p, st.p, part_rp);
+    launches += 4;
+}
+
 // what the reference still executes at the top of the iteration in which it breaks
 // (step 1 and step 2a, src/solver.cu:478-528): y is overwritten by the next half-step.
 void cuadmm_solver::enqueue_half_step() {
     SpmvEpilogue e;
     if (!asmc_valid) {
-        spmv_launch(*A, -1.0, SmC.p, 0.0, asmc.p, e, stream); ++launches;
-        if (world > 1) { comm->allreduce_sum(asmc.p, con_num, stream); ++launches; }
+        if (world == 1) { spmv_launch(*A, -1.0, SmC.p, 0.0, asmc.p, e, stream); ++launches; }
+        else reduce_partial_A(false, SmC.p, -1.0, nullptr, 0, nullptr);
     }
     rhsy_kernel<<<ew_grid(con_num, device), 256, 0, stream>>>(con_num, Rp.p, asmc.p, rhsy.p, st.p); ++launches;
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
@@ -530,8 +593,9 @@ void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double 
     h_st->switch_admm = sw;
     h_st->tau = sgs ? 1.95 : 1.618;
     CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
-    if (!sgs && X_best.n < std::max<int64_t>(vec_len, 1)) {
-        X_best.alloc(std::max<int64_t>(vec_len, 1)); y_best.alloc(std::max<int64_t>(con_num, 1)); S_best.alloc(std::max<int64_t>(vec_len, 1));
+    if (!sgs && X_best.n < std::max<int64_t>(nloc, 1)) {      // same size rule as solve(); the ADMM graph bakes these pointers
+        X_best.alloc(std::max<int64_t>(nloc, 1)); y_best.alloc(std::max<int64_t>(con_num, 1)); S_best.alloc(std::max<int64_t>(nloc, 1));
+        if (graph_admm) { cudaGraphExecDestroy(graph_admm); graph_admm = nullptr; }
     }
     for (auto e : prof_ev) cudaEventDestroy(e);
     prof_ev.clear();
@@ -561,16 +625,24 @@ void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double 
     h_st->done = 1;
     CUADMM_CUDA(cudaMemcpyAsync(&st.p->done, &h_st->done, sizeof(int), cudaMemcpyHostToDevice, stream));
     CUADMM_CUDA(cudaStreamSynchronize(stream));
+    if (peer) peer->check(stream);
 }
 
 // full-length X / S on every rank: scatter the owned ranges into a zeroed vector, sum all-reduce
 void cuadmm_solver::gather_full(const DevBuf<double>& local, double* h_full) {
     CUADMM_REQUIRE(initialised && h_full, "solver not initialised");
     CUADMM_CUDA(cudaSetDevice(device));
+    if (use_peer) {
+        // gather by owner: every rank stores its owned ranges into every rank's full-length vector (peer memory)
+        peer_scatter_full_launch(*peer, nloc, local.p, d_loc2glob.p, p_full, stream);
+        full_buf.download(h_full, vec_len, stream);
+        peer->check(stream);
+        return;
+    }
     if (full_buf.n < vec_len) full_buf.alloc(std::max<int64_t>(vec_len, 1));
     full_buf.zero(stream);
     scatter_full_kernel<<<ew_grid(nloc, device), 256, 0, stream>>>(nloc, local.p, d_loc2glob.p, full_buf.p);
-    comm->allreduce_sum(full_buf.p, vec_len, stream);
+    comm->allreduce_sum(full_buf.p, full_buf.p, vec_len, stream);
     full_buf.download(h_full, vec_len, stream);
     CUADMM_CUDA(cudaStreamSynchronize(stream));
 }
@@ -610,16 +682,15 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
         sub_kernel<<<gv, 256, 0, stream>>>(n, S.p, Cd.p, SmC.p);
         h_st->done = 0;
         CUADMM_CUDA(cudaMemcpyAsync(st.p, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+        CUADMM_CUDA(cudaStreamSynchronize(stream));      // h_st is mutated below: the copy must have read it first
         if (world == 1) {
             SpmvEpilogue e; e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = partial.p;
             spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream);
+            ++launches;
         } else {
-            SpmvEpilogue e;
-            spmv_launch(*A, 1.0, X.p, 0.0, red_buf.p, e, stream);
-            comm->allreduce_sum(red_buf.p, con_num, stream);
-            rp_kernel<<<nE_blocks, kEwThreads, 0, stream>>>(con_num, bd.p, red_buf.p, normA.p, y.p, Rp.p, st.p, partial.p);
+            reduce_partial_A(true, X.p, 1.0, nullptr, 0, partial.p);
         }
-        launches += 5;
+        launches += 4;
     }
     h_st->iter = 1;
     h_st->max_iter = max_iter; h_st->stop_tol = stop_tol;
@@ -698,6 +769,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     cudaEventElapsedTime(&ms, ev_start, ev_now);
     total_time = ms / 1000.0;
     solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (peer) peer->check(stream);
     if (verbose) {
         printf("\n -------------------------------------------------------------------------------\n\n");
         printf("%s\n", h_st->stop_reason == 2 ? "Solver ended: maximum iteration reached" : "Solver ended: converged.");
@@ -777,6 +849,15 @@ int cuadmm_solver_set_distributed(cuadmm_solver_t* s, int rank, int world, const
         CUADMM_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
         s->rank = rank; s->world = world;
         memcpy(s->nccl_id, id, 128);
+    });
+}
+
+int cuadmm_solver_set_device(cuadmm_solver_t* s, int device) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s, "solver is null");
+        CUADMM_REQUIRE(!s->initialised, "set_device must precede init");
+        CUADMM_REQUIRE(device >= 0, "negative device index");
+        s->device = device; s->device_set = true;
     });
 }
 

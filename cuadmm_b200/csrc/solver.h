@@ -10,6 +10,8 @@
 #include "problem.h"
 #include "shard.h"
 #include "dist.h"
+#include "peer.h"
+#include "peer_kernels.h"
 
 namespace cuadmm {
 
@@ -40,11 +42,22 @@ struct cuadmm_solver {
     int rank = 0, world = 1;
     char nccl_id[128] = {0};
     cuadmm::Shard shard;
+    // transport of the partial products: peer memory (default; kernels store into the peers' arenas, peer.h) or
+    // NCCL all-reduce (CUADMM_COMM=nccl)
+    bool use_peer = true;
+    bool device_set = false;                 // cuadmm_solver_set_device / CUADMM_DEVICE given
+    std::unique_ptr<cuadmm::PeerComm> peer;
+    int64_t slice = 0;                       // rows of an m-vector reduced by one rank (peer transport)
+    double* stage = nullptr;                 // arena: world x slice staged partial rows addressed to this rank
+    cuadmm::PeerPtrs p_stage, p_asmc, p_Rp, p_full;
+    cuadmm::DevBuf<double> cta_part;         // per-CTA partial sums of peer_reduce_kernel
     std::unique_ptr<cuadmm::NcclComm> comm;
-    cuadmm::DevBuf<double> red_buf;          // m + 2 doubles: partial A_g x_g + two scalars, all-reduced in place
+    cuadmm::DevBuf<double> red_buf;          // NCCL: m + 2 doubles: partial A_g x_g + two scalars, all-reduced in place
+    cuadmm::DevBuf<double> asmc_part;        // NCCL: this rank's partial -A_g (S-C)_g (all-reduced into asmc)
     cuadmm::DevBuf<int64_t> d_loc2glob;
     cuadmm::DevBuf<double> full_buf;         // vec_len doubles, for gathering full X / S
     void gather_full(const cuadmm::DevBuf<double>& local, double* h_full);
+    void reduce_partial_A(bool for_rp, const double* x_local, double alpha, const double* part_rd, int n_rd, double* part_rp);
     std::unique_ptr<cuadmm_plan> plan;
     cuadmm_spmv_s* A = nullptr;    // m x vec_len (row-normalised)
     cuadmm_spmv_s* At = nullptr;   // vec_len x m

@@ -55,6 +55,11 @@ __device__ __forceinline__ void spmv_store(const SpmvEpilogue& e, double alpha, 
             acc1 = fma(b, e.aux3[i], acc1);              // <b, y>
             break;
         }
+        case 5: {  // partial row of this rank -> staging slot [rank] of the rank that reduces row i
+            const unsigned q = (unsigned)i / e.slice;
+            e.push[q][(size_t)e.rank * e.slice + ((unsigned)i - q * e.slice)] = alpha * r;
+            break;
+        }
     }
 }
 

@@ -22,6 +22,8 @@ struct SpmvEpilogue {
     // mode 2: Rd1 = At*y - C; Xb = X + sig*Rd1   y(=Rd1) = r - aux1[i]; out2[i] = aux2[i] + sig*y   (:514-527)
     // mode 3: Rd1 = r - C; Rd = Rd1 + S; X += tau*sig*Rd; partial sums of |Rd|^2 and <C,X>   (:721-758,775-776)
     // mode 4: Rp = b - A*X; partial sums of |normA*Rp|^2                                       (:764-772)
+    // mode 5: sharded solver, fused with the reduction over ranks: the partial row alpha*r is stored straight into the
+    //         staging area of the rank that reduces row i (push[i / slice], peer memory over NVLink; see peer.h)
     int mode = 0;
     const double* aux1 = nullptr;
     const double* aux2 = nullptr;
@@ -30,6 +32,9 @@ struct SpmvEpilogue {
     double* out3 = nullptr;
     const double* scal = nullptr;   // device scalars (sig, tau, ...) — see solver state layout
     double* partial = nullptr;      // per-CTA partial sums (2 per CTA), deterministic two-stage reduction
+    double* push[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // mode 5: staging area of every rank
+    unsigned slice = 1;             // mode 5: rows reduced by one rank
+    int rank = 0;                   // mode 5: this rank
 };
 
 void spmv_launch(const cuadmm_spmv_s& A, double alpha, const double* x, double beta, double* y,

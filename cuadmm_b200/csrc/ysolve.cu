@@ -365,18 +365,30 @@ __global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t
 // are read (tile_ptr / tile_col: per tile row, runs of consecutive non-empty tiles as column
 // ranges): the inverse of the trailing factor block inherits
 // the block structure of the separators it came from and is often half empty.
-__global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double* __restrict__ T, const double* __restrict__ in,
+// Sharded solver (npush > 0): this rank computes rows [row0, row0 + nrows) only and stores each result into every
+// rank's copy of `out` (and of the scattered y) over peer memory; the kernel ends with the peer_leave handshake, so
+// when it retires every rank holds the complete vector.  No peer_enter is needed: a peer can only reach this
+// kernel after the handshake of the previous one, which this rank joined after its last read of the buffers.
+__global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double* __restrict__ T, const double* in,
                                                         double* out, const int32_t* __restrict__ tile_ptr,
                                                         const int32_t* __restrict__ tile_col, double* out_scatter,
                                                         const int32_t* __restrict__ out_perm, int64_t perm_base,
-                                                        const int* __restrict__ done_flag, int longest_last) {
+                                                        const int* __restrict__ done_flag, int longest_last,
+                                                        int64_t row0, int64_t nrows, int npush, PeerView pv,
+                                                        PeerPtrs outp, PeerPtrs scatp) {
     if (done_flag && *done_flag) return;
     const int lane = threadIdx.x & 31;
+    unsigned long long ep = 0;
+    if (npush) ep = peer_epoch(pv);
     // the CTAs with the longest rows go first (lower-triangular storage: the last rows), so the grid's tail
     // wave is made of short rows
     const int64_t cta = longest_last ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
-    const int64_t row = cta * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= r) return;
+    const int64_t lrow = cta * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (lrow >= nrows) {
+        if (npush) peer_leave(pv, ep);
+        return;
+    }
+    const int64_t row = row0 + lrow;
     const double* Ti = T + row * r;
     const int I = (int)(row >> 6);
     double acc0 = 0.0, acc1 = 0.0;
@@ -404,9 +416,18 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
-        out[row] = acc;
-        if (out_scatter) out_scatter[out_perm[perm_base + row]] = acc;
+        if (npush == 0) {
+            out[row] = acc;
+            if (out_scatter) out_scatter[out_perm[perm_base + row]] = acc;
+        } else {
+            for (int q = 0; q < npush; ++q) outp.p[q][row] = acc;
+            if (out_scatter) {
+                const int32_t d = out_perm[perm_base + row];
+                for (int q = 0; q < npush; ++q) scatp.p[q][d] = acc;
+            }
+        }
     }
+    if (npush) peer_leave(pv, ep);
 }
 
 // gather/external fold, then the packed CTA-per-subtree kernel on `st` and the warp-per-subtree kernel
@@ -1059,9 +1080,12 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
             }
             ptr.push_back((int32_t)(col.size() / 2));
         };
+        Y->h_tail_cost[0].assign(nt, 0.0); Y->h_tail_cost[1].assign(nt, 0.0);
         for (int I = 0; I < nt; ++I) {
             add_runs(tp, tc, 0, I + 1, [&](int J) { return flags[(size_t)I * nt + J] != 0; });       // L22^-1: lower
             add_runs(tpt, tct, I, nt, [&](int J) { return flags[(size_t)J * nt + I] != 0; });       // its transpose: upper
+            for (int32_t t = tp[I]; t < tp[I + 1]; ++t) Y->h_tail_cost[0][I] += tc[2 * t + 1] - tc[2 * t];
+            for (int32_t t = tpt[I]; t < tpt[I + 1]; ++t) Y->h_tail_cost[1][I] += tct[2 * t + 1] - tct[2 * t];
         }
         if (tc.empty()) tc.assign(2, 0);
         if (tct.empty()) tct.assign(2, 0);
@@ -1090,21 +1114,62 @@ cuadmm_ysolve_s::~cuadmm_ysolve_s() {
     if (streams.side) cudaStreamDestroy(streams.side);
 }
 
+void cuadmm_ysolve_s::enable_peer(const PeerComm* pc, size_t off_tmp, size_t off_x) {
+    peer = pc;
+    peer_tmp = pc->ptrs(off_tmp);
+    peer_x = pc->ptrs(off_x);
+    tail_tmp_p = pc->local<double>(off_tmp);
+    x_p = pc->local<double>(off_x);
+    // rows of each tail GEMV split into `world` contiguous ranges of equal work (columns read)
+    for (int k = 0; k < 2; ++k) {
+        const std::vector<double>& c = h_tail_cost[k];
+        double total = 0.0;
+        for (int64_t i = 0; i < n_tail; ++i) total += c[i >> 6] + 32.0;
+        std::vector<int64_t> cut(pc->world + 1, n_tail);
+        cut[0] = 0;
+        double acc = 0.0;
+        int q = 1;
+        for (int64_t i = 0; i < n_tail && q < pc->world; ++i) {
+            acc += c[i >> 6] + 32.0;
+            while (q < pc->world && acc >= total * q / pc->world) cut[q++] = i + 1;
+        }
+        tail_row0[k] = cut[pc->rank]; tail_row1[k] = cut[pc->rank + 1];
+    }
+}
+
 void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st) {
     if (m == 0) return;
+    double* xv = x_p ? x_p : x.p;
+    double* tmpv = tail_tmp_p ? tail_tmp_p : tail_tmp.p;
     // forward: z = L11^-1 P rhs (lead), z_tail = P rhs - L21 z_lead
     launch_sweep(fwd, d_rhs_, perm.p, z.p, nullptr, nullptr, done_flag, st, streams);
     if (n_tail > 0) {
-        const int blocks = (int)((n_tail + 7) / 8);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
-        tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tail_tmp.p, tail_tptr.p, tail_tcol.p,
-                                                 nullptr, nullptr, 0, done_flag, 1);
-        tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tail_tmp.p, x.p + n_lead, tail_tptr_t.p, tail_tcol_t.p,
-                                                 d_y_, perm.p, n_lead, done_flag, 0);
+        if (!peer || peer->world == 1) {
+            const int blocks = (int)((n_tail + 7) / 8);
+            tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p, tail_tcol.p,
+                                                     nullptr, nullptr, 0, done_flag, 1, 0, n_tail, 0, PeerView(), PeerPtrs(), PeerPtrs());
+            tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p, tail_tcol_t.p,
+                                                     d_y_, perm.p, n_lead, done_flag, 0, 0, n_tail, 0, PeerView(), PeerPtrs(), PeerPtrs());
+        } else {
+            // y must live in the peer arena: the same offset in every rank's arena
+            const char* yb = reinterpret_cast<const char*>(d_y_);
+            const char* lb = peer->base[peer->rank];
+            CUADMM_REQUIRE(yb >= lb && yb + sizeof(double) * m <= lb + peer->bytes, "sharded y-solve: y is not in the peer arena");
+            const PeerPtrs py = peer->ptrs((size_t)(yb - lb));
+            PeerPtrs pxt = peer_x;
+            for (int q = 0; q < peer->world; ++q) pxt.p[q] += n_lead;
+            const PeerView pv = peer->view();
+            const int64_t n0 = tail_row1[0] - tail_row0[0], n1 = tail_row1[1] - tail_row0[1];
+            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n0 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p,
+                tail_tcol.p, nullptr, nullptr, 0, done_flag, 1, tail_row0[0], n0, peer->world, pv, peer_tmp, PeerPtrs());
+            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n1 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p,
+                tail_tcol_t.p, d_y_, perm.p, n_lead, done_flag, 0, tail_row0[1], n1, peer->world, pv, pxt, py);
+        }
         CUADMM_CUDA(cudaGetLastError());
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y
-    launch_sweep(bwd, z.p, nullptr, x.p, d_y_, perm.p, done_flag, st, streams);
+    launch_sweep(bwd, z.p, nullptr, xv, d_y_, perm.p, done_flag, st, streams);
 }
 
 extern "C" {

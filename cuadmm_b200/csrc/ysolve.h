@@ -2,6 +2,7 @@
 #pragma once
 #include "common.h"
 #include "chol_host.h"
+#include "peer.h"
 
 namespace cuadmm {
 
@@ -65,6 +66,15 @@ struct cuadmm_ysolve_s {
     cuadmm::DevBuf<int32_t> tail_tptr, tail_tcol, tail_tptr_t, tail_tcol_t;   // non-empty 64-column tiles per tile row (CSR)
     cuadmm::DevBuf<double> d_rhs, d_y; // staging for the host entry
     std::vector<int32_t> h_perm;
+    // sharded solver (peer.h): the rows of the two dense-tail GEMVs are split over the ranks by work; every rank
+    // stores its rows straight into every rank's tail_tmp / x / y (all three live in the peer arena then)
+    const cuadmm::PeerComm* peer = nullptr;
+    double* tail_tmp_p = nullptr;       // == tail_tmp.p, or the arena copy
+    double* x_p = nullptr;              // == x.p, or the arena copy
+    cuadmm::PeerPtrs peer_tmp, peer_x;
+    int64_t tail_row0[2] = {0, 0}, tail_row1[2] = {0, 0};   // this rank's rows of L22^-1 / L22^-T
+    std::vector<double> h_tail_cost[2]; // per 64-row tile row: columns read (work per row)
+    void enable_peer(const cuadmm::PeerComm* pc, size_t off_tmp, size_t off_x);
     const int* done_flag = nullptr;
     cuadmm::SweepStreams streams;
     ~cuadmm_ysolve_s();
