@@ -4,7 +4,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcuadmm_b200.so")
+LIB_PATH = os.environ.get("CUADMM_LIB_PATH") or os.path.join(_HERE, "lib", "libcuadmm_b200.so")   # override: A/B builds in experiments
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `make` at the repo root (or "
@@ -529,3 +529,41 @@ class Solver:
         _check(lib.cuadmm_solver_ysolve_stats(self.h, _p(s, c_i64p)))
         return dict(nnz_AAt=int(s[0]), nnz_L=int(s[1]), levels=int(s[2]), dense_tail=int(s[3]),
                     launches=int(s[4]), bytes=int(s[5]), deficient=int(s[6]))
+
+
+# ---------------------------------------------------------------- MEX-shaped entry
+_maybe("cuadmm_solve_matlab_like", C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64,
+       c_i64p, c_i64p, c_f64p, c_i64p, c_f64p, C.c_int64, c_i64p, c_f64p, C.c_int64, c_f64p, C.c_int64,
+       c_f64p, c_f64p, c_f64p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+       c_f64p, c_f64p, c_f64p, c_i64p, c_f64p, c_f64p)
+
+
+def solve_matlab_like(eig_stream_num_per_gpu, max_iter, stop_tol, At_jc, At_ir, At_pr, b_ir, b_pr, C_ir, C_pr, blk_vec,
+                      X0, y0, S0, sig, sig_update_threshold=500, sig_update_stage_1=50, sig_update_stage_2=100,
+                      switch_admm=11000, sigscale=1.05):
+    """cuadmm_solve_matlab_like: the argument list of the reference's MEX gateway (MATLAB/cuadmm_MATLAB.cu:197-433):
+    At_stack as MATLAB sparse (jc/ir size_t, pr double), b and C_stack as sparse columns, blk_vec as doubles,
+    X0/y0/S0 dense.  Returns (X, y, S, info) with info = {iter_num, pobj, dobj, errRp, errRd, relgap, sig, bscale,
+    Cscale, total_time} like the 10 x 2 info cell (:157-183)."""
+    jc, ir, pr = _i64(At_jc), _i64(At_ir), _f64(At_pr)
+    bi, bp, ci, cp = _i64(b_ir), _f64(b_pr), _i64(C_ir), _f64(C_pr)
+    blk = _f64(blk_vec)
+    con_num = len(jc) - 1
+    vec_len = int(sum(int(n) * (int(n) + 1) // 2 for n in blk))
+    X0, y0, S0 = _f64(X0), _f64(y0), _f64(S0)
+    X = np.zeros(vec_len); y = np.zeros(con_num); S = np.zeros(vec_len)
+    it = C.c_int64(0); tt = C.c_double(0.0)
+    info = np.zeros(8 * (max_iter + 1))
+    _check(lib.cuadmm_solve_matlab_like(eig_stream_num_per_gpu, max_iter, stop_tol, vec_len, con_num,
+                                        _p(jc, c_i64p), _p(ir, c_i64p), _p(pr, c_f64p), _p(bi, c_i64p), _p(bp, c_f64p), len(bp),
+                                        _p(ci, c_i64p), _p(cp, c_f64p), len(cp), _p(blk, c_f64p), len(blk),
+                                        _p(X0, c_f64p), _p(y0, c_f64p), _p(S0, c_f64p), sig,
+                                        sig_update_threshold, sig_update_stage_1, sig_update_stage_2, switch_admm, sigscale,
+                                        _p(X, c_f64p), _p(y, c_f64p), _p(S, c_f64p), C.byref(it), _p(info, c_f64p), C.byref(tt)))
+    n = int(it.value)
+    H = info.reshape(8, max_iter + 1)
+    names = ["pobj", "dobj", "errRp", "errRd", "relgap", "sig", "bscale", "Cscale"]
+    out = {k: H[i, :n].copy() for i, k in enumerate(names)}
+    out["iter_num"] = n
+    out["total_time"] = float(tt.value)
+    return X, y, S, out

@@ -337,10 +337,17 @@ std::vector<int64_t> find_supernodes(const CholFactor& F, int64_t max_size) {
 // ------------------------------------------------------------------------------------------
 // numeric up-looking Cholesky on the symbolic structure
 // ------------------------------------------------------------------------------------------
-static constexpr double kPivotTol = 1e-11;
+// Relative pivot tolerance: a pivot d_k <= tol * M_kk marks constraint k as redundant (see below).  The default keeps
+// every pivot that stands clear of the rounding noise of the factorisation (the reference keeps them all: CHOLMOD
+// LDL^T of A A^T + 1e-15 I); CUADMM_PIVOT_TOL overrides it.
+double pivot_tol() {
+    if (const char* e = getenv("CUADMM_PIVOT_TOL")) { const double v = atof(e); if (v > 0.0 && v < 1.0) return v; }
+    return 1e-11;
+}
 
 void chol_numeric(const SymCsc& C, CholFactor& F, int64_t n_lead) {
     F.n_deficient = 0;
+    const double kPivotTol = pivot_tol();
     const int64_t n = F.n;
     std::vector<int64_t> rp; std::vector<int32_t> rj; std::vector<double> rx;
     lower_rows(C, rp, rj, rx);

@@ -50,7 +50,8 @@ std::vector<int64_t> find_supernodes(const CholFactor& F, int64_t max_size);
 void chol_symbolic(const SymCsc& M, const std::vector<int32_t>& perm, CholFactor& F, SymCsc* permuted = nullptr);
 // numeric up-looking factorisation of rows [0, n_lead); for rows >= n_lead only the entries in
 // columns < n_lead are computed (the trailing Schur complement is left to the caller).
-// Pivots <= 1e-11 * M_kk mark redundant constraints (see chol_host.cpp), they do not throw.
+// Pivots <= pivot_tol() * M_kk mark redundant constraints (see chol_host.cpp), they do not throw.
+double pivot_tol();
 void chol_numeric(const SymCsc& Mperm, CholFactor& F, int64_t n_lead);
 
 }  // namespace cuadmm

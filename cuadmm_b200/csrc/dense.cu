@@ -293,7 +293,7 @@ void build_dense_tail(const SymCsc& C, const CholFactor& F, int64_t n_lead, int6
     info.zero(st);
     std::vector<double> h_floor(r, 0.0);
     for (int64_t j = n_lead; j < n_lead + r; ++j)
-        for (int64_t p = C.p[j]; p < C.p[j + 1]; ++p) if (C.i[p] == j) h_floor[j - n_lead] = 1e-11 * C.x[p];
+        for (int64_t p = C.p[j]; p < C.p[j + 1]; ++p) if (C.i[p] == j) h_floor[j - n_lead] = pivot_tol() * C.x[p];
     DevBuf<double> d_floor; d_floor.upload(h_floor, st);
     potrf_lower(st, r, S.p, r, inv_diag.p, info.p, d_floor.p);
     int h_info = 0;

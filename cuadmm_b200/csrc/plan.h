@@ -40,8 +40,9 @@ struct cuadmm_plan {
     cuadmm::DevBuf<double> d_Q;
     bool warm_start = true;
     void reset_warm_start();
-    double threshold = 1e-11;
+    double threshold = 1e-11;     // columns of G count as orthogonal when every |cos| <= threshold (tested on the state after each sweep)
     int max_sweeps = 40;
+    bool use_gram = true;         // CUADMM_JACOBI_GRAM=0: round-1 stopping rule (a whole sweep without a cosine above the threshold)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> side_streams;    // classes run concurrently on these
     std::vector<cudaEvent_t> side_events;

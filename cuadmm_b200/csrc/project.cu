@@ -62,14 +62,28 @@ __device__ __forceinline__ double mat_max(double v, double* red, int tid) {
 // Column stride ld == L (mod 16) makes the L-row windows of the 16/L consecutive round-robin
 // columns a half-warp touches fall into disjoint banks.
 // ------------------------------------------------------------------------------------------
+// 16-byte sweep accesses (two rows per lane) were measured 10 % SLOWER than the 8-byte ones on B200 (the ld == 8 mod 16
+// layout they need costs the other phases their conflict-free column windows): off by default, kept for experiments
+#ifndef CUADMM_JACOBI_VEC
+#define CUADMM_JACOBI_VEC 0
+#endif
 __host__ __device__ __forceinline__ int jacobi_ld(int n, int L) {
     if (L >= 16) return n | 1;
+    // L == 4: the sweep moves two rows per lane with 16-byte shared-memory accesses; a quarter-warp (two pairs' groups,
+    // 64 contiguous bytes each) is conflict-free when consecutive round-robin columns are 64 bytes apart mod 128:
+    // ld == 8 (mod 16).  L == 8: 8-byte accesses, ld == 8 (mod 16) as before.
+#if CUADMM_JACOBI_VEC
+    const int want = 8;
+#else
+    const int want = L & 15;
+#endif
     int ld = n;
-    while ((ld & 15) != (L & 15)) ++ld;
+    while ((ld & 15) != want) ++ld;
     return ld;
 }
 __host__ __device__ __forceinline__ size_t jacobi_per_mat(int nmax, int L) {
-    return (size_t)jacobi_ld(nmax, L) * nmax + nmax + (nmax + 2) / 2 + 1 + 34;
+    // even number of doubles: every matrix of a multi-matrix CTA starts 16-byte aligned (vectorised sweeps)
+    return (((size_t)jacobi_ld(nmax, L) * nmax + nmax + (nmax + 2) / 2 + 1 + 34) + 1) & ~(size_t)1;
 }
 
 // rotation from (alpha, beta, gamma) with two rsqrt: cos(2t) = |d|/h, sin(2t) = sign(d) 2gamma/h,
@@ -90,6 +104,72 @@ __device__ __forceinline__ void jacobi_cs2(double alpha, double beta, double gam
     const double x = s2 * gamma;                          // 2 c s gamma
     alpha_new = fma(cc, alpha, fma(ss, beta, -x));
     beta_new = fma(ss, alpha, fma(cc, beta, x));
+}
+
+__device__ __forceinline__ void jacobi_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Convergence test on the STATE of the block: are all columns of G mutually orthogonal to `thr` (relative)?
+// The Gram matrix G^T G is formed 8 x 8 tile by tile on the FP64 tensor cores (mma.sync.m8n8k4: n^3/2 MACs in
+// n^3/512 warp instructions — about 2 % of one sweep) and every off-diagonal entry is held against the tracked squared
+// norms w[].  Testing the state after a sweep, instead of the cosines met during the next one, saves the whole
+// verification sweep the rotation loop used to end with (1 of ~3 in the warm-started regime).
+// Entries below 1e-15 in absolute value (G has norm ~1) are rounding noise of null columns and never count.
+template <int NT, bool WARP>
+__device__ __forceinline__ bool jacobi_gram_converged(const double* G, const double* w, int n, int ld, double thr2, int tid) {
+    const int lane = tid & 31;
+    const int wid = WARP ? 0 : (tid >> 5);
+    constexpr int NW = WARP ? 1 : NT / 32;
+    const int nt = (n + 7) >> 3;
+    const int kr = lane & 3, cq = lane >> 2;
+    int flag = 0;
+    // a warp takes row tiles P = wid, wid + NW, ... and walks the column tiles Q >= P four at a time: four independent
+    // accumulator pairs per k-step hide the latency of the dependent mma chain (measured: 20 % of the kernel's stall
+    // samples sat on a single-accumulator chain)
+    for (int P = wid; P < nt; P += NW) {
+        const int pcol = P * 8 + cq;
+        const double* Gp = G + (size_t)min(pcol, n - 1) * ld;
+        const bool pv = pcol < n;
+        const int row = P * 8 + cq;
+        const double wr = (row < n) ? w[row] : 0.0;
+        for (int Q0 = P; Q0 < nt; Q0 += 4) {
+            double c[4][2];
+            const double* Gq[4];
+            bool qv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int qcol = (Q0 + u) * 8 + cq;
+                qv[u] = (Q0 + u < nt) && qcol < n;
+                Gq[u] = G + (size_t)min(qcol, n - 1) * ld;
+                c[u][0] = 0.0; c[u][1] = 0.0;
+            }
+            for (int r0 = 0; r0 < n; r0 += 4) {
+                const int r = r0 + kr;
+                const bool rv = r < n;
+                const double av = (pv && rv) ? Gp[r] : 0.0;
+                double bv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bv[u] = (qv[u] && rv) ? Gq[u][r] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) jacobi_dmma(c[u][0], c[u][1], av, bv[u]);
+            }
+            // c[u] = (G^T G)[P*8 + lane/4][(Q0+u)*8 + 2*(lane%4) + {0,1}]
+            if (row < n) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int col0 = (Q0 + u) * 8 + 2 * kr;
+                    if (Q0 + u < nt) {
+                        if (col0 < n && col0 != row) { const double g2 = c[u][0] * c[u][0]; if (g2 > thr2 * wr * w[col0] && g2 > 1e-30) flag = 1; }
+                        if (col0 + 1 < n && col0 + 1 != row) { const double g2 = c[u][1] * c[u][1]; if (g2 > thr2 * wr * w[col0 + 1] && g2 > 1e-30) flag = 1; }
+                    }
+                }
+            }
+        }
+    }
+    const int any = WARP ? __any_sync(0xffffffffu, flag) : __syncthreads_or(flag);
+    return !any;
 }
 
 template <int T, int L, int RPL, bool WARP>
@@ -180,25 +260,54 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     // held in registers, so the product is formed in place.
     double* Qb = a.Q ? a.Q + d.q_off : nullptr;
     if (Qb) {
-        for (int r = grp; r < n; r += NG) {
-            double arow[RPL];
+        // FP64 tensor cores (mma.sync.m8n8k4): every warp owns strips of 8 rows of G; the strip (8 x n) is held as A
+        // fragments in registers, multiplied by the 8-column tiles of Q streamed from global memory / L2 (one 8-byte load
+        // per lane feeds 256 MACs) and written back over itself — rows are independent, so the product is in place.
+        constexpr int KF = (((L * RPL) > 168 ? 168 : (L * RPL)) + 3) / 4;   // k-fragments per lane for the largest n of the variant
+        constexpr int NWARP = WARP ? 1 : NT / 32;
+        const int wid = WARP ? 0 : (tid >> 5);
+        const int l32 = tid & 31;
+        const int fr = l32 >> 2, fk = l32 & 3;
+        const int nk = (n + 3) >> 2;
+        for (int r0 = wid * 8; r0 < n; r0 += NWARP * 8) {
+            const int row = r0 + fr;
+            double af[KF];
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) {
-                const int k = lane + i * L;
-                arow[i] = (k < n) ? G[r + k * ld] : 0.0;
+            for (int kk = 0; kk < KF; ++kk) {
+                const int k = kk * 4 + fk;
+                af[kk] = (kk < nk && row < n && k < n) ? G[row + k * ld] : 0.0;
             }
-            __syncwarp(gmask);
-            for (int j = 0; j < n; ++j) {
-                const double* __restrict__ qj = Qb + (size_t)j * n;
-                double acc = 0.0;
+            __syncwarp();                                   // the whole strip is in registers before any of it is overwritten
+            for (int j0 = 0; j0 < n; j0 += 32) {            // four 8-column tiles at a time: independent accumulators
+                const double* __restrict__ qc[4];
+                bool cv[4];
+                double c[4][2];
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) {
-                    const int k = lane + i * L;
-                    if (k < n) acc = fma(arow[i], __ldg(qj + k), acc);
+                for (int u = 0; u < 4; ++u) {
+                    const int col = j0 + 8 * u + fr;
+                    cv[u] = col < n;
+                    qc[u] = Qb + (size_t)min(col, n - 1) * n;
+                    c[u][0] = 0.0; c[u][1] = 0.0;
                 }
 #pragma unroll
-                for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-                if (lane == 0) G[r + j * ld] = acc;
+                for (int kk = 0; kk < KF; ++kk) {
+                    if (kk < nk) {
+                        const int k = kk * 4 + fk;
+                        double bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) bv[u] = (cv[u] && k < n) ? __ldg(qc[u] + k) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) jacobi_dmma(c[u][0], c[u][1], af[kk], bv[u]);
+                    }
+                }
+                if (row < n) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int cc = j0 + 8 * u + 2 * fk;
+                        if (cc < n) G[row + cc * ld] = c[u][0];
+                        if (cc + 1 < n) G[row + (cc + 1) * ld] = c[u][1];
+                    }
+                }
             }
         }
         mat_sync<WARP>();
@@ -213,7 +322,9 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     const double tiny2 = 1.2325951644078309e-32;  // 2^-106: rotations below rounding level are skipped
     int sweeps = 0;
     bool converged = false;
-    while (sweeps < a.max_sweeps) {
+    // L == 4: two adjacent rows per lane and access (16-byte shared-memory loads / stores): row pair (2*lane + 2*L*i)
+    constexpr bool VEC = CUADMM_JACOBI_VEC && (L == 4) && (RPL % 2 == 0);
+    while (true) {
         // refresh the tracked squared norms from the data
         for (int j = grp; j < n; j += NG) {
             const double* Gj = G + j * ld;
@@ -224,6 +335,8 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
             if (lane == 0) w[j] = al;
         }
         mat_sync<WARP>();
+        if (a.use_gram && jacobi_gram_converged<NT, WARP>(G, w, n, ld, thr2, tid)) { converged = true; break; }
+        if (sweeps >= a.max_sweeps) break;
         int big = 0;
         for (int step = 0; step < m - 1; ++step) {
             for (int k = grp; k < half; k += NG) {
@@ -234,18 +347,36 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
                 double* __restrict__ Gp = G + p * ld;
                 double* __restrict__ Gq = G + q * ld;
                 double gp[RPL], gq[RPL];
-                double ga = 0.0;
+                double ga = 0.0, gb = 0.0;
+                if (VEC) {
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) {
-                    const int r = lane + i * L;
-                    if (r < n) {
-                        gp[i] = Gp[r];
-                        gq[i] = Gq[r];
-                        ga = fma(gp[i], gq[i], ga);
-                    } else {
-                        gp[i] = 0.0; gq[i] = 0.0;
+                    for (int i = 0; i < RPL / 2; ++i) {
+                        const int r = 2 * (lane + i * L);
+                        if (r < n) {             // ld is even and G is zero-free beyond n only up to ld: row r + 1 < ld always
+                            const double2 vp = *reinterpret_cast<const double2*>(Gp + r);
+                            const double2 vq = *reinterpret_cast<const double2*>(Gq + r);
+                            gp[2 * i] = vp.x; gq[2 * i] = vq.x;
+                            gp[2 * i + 1] = (r + 1 < n) ? vp.y : 0.0; gq[2 * i + 1] = (r + 1 < n) ? vq.y : 0.0;
+                            ga = fma(gp[2 * i], gq[2 * i], ga);
+                            gb = fma(gp[2 * i + 1], gq[2 * i + 1], gb);
+                        } else {
+                            gp[2 * i] = 0.0; gq[2 * i] = 0.0; gp[2 * i + 1] = 0.0; gq[2 * i + 1] = 0.0;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) {
+                        const int r = lane + i * L;
+                        if (r < n) {
+                            gp[i] = Gp[r];
+                            gq[i] = Gq[r];
+                            if (i & 1) gb = fma(gp[i], gq[i], gb); else ga = fma(gp[i], gq[i], ga);
+                        } else {
+                            gp[i] = 0.0; gq[i] = 0.0;
+                        }
                     }
                 }
+                ga += gb;
                 const double al = w[p], be = w[q];
 #pragma unroll
                 for (int o = L / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(gmask, ga, o);
@@ -254,12 +385,28 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
                 if (g2 > tiny2 * ab) {
                     double c, sn, an, bn;
                     jacobi_cs2(al, be, ga, c, sn, an, bn);
+                    if (VEC) {
 #pragma unroll
-                    for (int i = 0; i < RPL; ++i) {
-                        const int r = lane + i * L;
-                        if (r < n) {
-                            Gp[r] = fma(c, gp[i], -sn * gq[i]);
-                            Gq[r] = fma(sn, gp[i], c * gq[i]);
+                        for (int i = 0; i < RPL / 2; ++i) {
+                            const int r = 2 * (lane + i * L);
+                            if (r < n) {
+                                double2 op, oq;
+                                op.x = fma(c, gp[2 * i], -sn * gq[2 * i]);
+                                oq.x = fma(sn, gp[2 * i], c * gq[2 * i]);
+                                op.y = fma(c, gp[2 * i + 1], -sn * gq[2 * i + 1]);
+                                oq.y = fma(sn, gp[2 * i + 1], c * gq[2 * i + 1]);
+                                *reinterpret_cast<double2*>(Gp + r) = op;
+                                *reinterpret_cast<double2*>(Gq + r) = oq;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < RPL; ++i) {
+                            const int r = lane + i * L;
+                            if (r < n) {
+                                Gp[r] = fma(c, gp[i], -sn * gq[i]);
+                                Gq[r] = fma(sn, gp[i], c * gq[i]);
+                            }
                         }
                     }
                     if (lane == 0) { w[p] = an; w[q] = bn; }
@@ -268,8 +415,11 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
             mat_sync<WARP>();
         }
         ++sweeps;
-        const int any_big = WARP ? __any_sync(0xffffffffu, big) : __syncthreads_or(big);
-        if (!any_big) { converged = true; break; }
+        if (!a.use_gram) {
+            // rule of round 1: stop after a sweep that met no cosine above the threshold
+            const int any_big = WARP ? __any_sync(0xffffffffu, big) : __syncthreads_or(big);
+            if (!any_big) { converged = true; break; }
+        }
     }
 
     // ---- eigenvalues from the column norms; weights of the positive part ----
@@ -676,6 +826,8 @@ void cuadmm_plan::build_device() {
     d_sweeps.alloc(std::max<int64_t>(nblk, 1));
     warm_start = true;
     if (const char* e = getenv("CUADMM_JACOBI_WARM")) warm_start = atoi(e) != 0;
+    if (const char* e = getenv("CUADMM_JACOBI_GRAM")) use_gram = atoi(e) != 0;
+    if (const char* e = getenv("CUADMM_JACOBI_THR")) { const double v = atof(e); if (v > 0.0 && v < 1e-3) threshold = v; }
     if (warm_start && q_total > 0) {
         d_Q.alloc(q_total);
         reset_warm_start();
@@ -726,7 +878,10 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
     if (device < 0) throw Error(CUADMM_ENODEVICE, "plan was built without a CUDA device; there is no CPU fallback");
     int launches = 0;
     // blocks on the dense path produce no eigenvalues: their debug slots read NaN
-    if (want_eig) CUADMM_CUDA(cudaMemsetAsync(d_eig.p, 0xFF, sizeof(double) * (size_t)d_eig.n, stream));
+    if (want_eig) {
+        CUADMM_CUDA(cudaMemsetAsync(d_eig.p, 0xFF, sizeof(double) * (size_t)d_eig.n, stream));
+        CUADMM_CUDA(cudaMemsetAsync(d_sweeps.p, 0, sizeof(int32_t) * (size_t)d_sweeps.n, stream));
+    }
     // fork: the dense (GEMM) part, if any, runs on the caller's stream; Jacobi classes run on side
     // streams so that small, mid and large blocks overlap (class 0 stays on the caller's stream when
     // there is no dense part)
@@ -750,6 +905,7 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
         a.sweeps_out = want_eig ? d_sweeps.p : nullptr;
         a.scratch = d_scratch.p;
         a.done_flag = done_flag;
+        a.use_gram = use_gram ? 1 : 0;
         a.Q = (warm_start && cl.kind != kGlobalKind && d_Q.n > 0) ? d_Q.p : nullptr;
         if (epi) a.epi = *epi; else { a.epi.X = nullptr; a.epi.Rd1 = nullptr; a.epi.Cd = nullptr; a.epi.S = nullptr; a.epi.SmC = nullptr; a.epi.sig_ptr = nullptr; }
         if (cl.kind == kGlobalKind) {

@@ -65,6 +65,7 @@ struct ProjArgs {
     int32_t* sweeps_out;    // optional (null): sweeps used, at desc.index
     double* scratch;        // global variant
     const int* done_flag;   // optional device flag: kernels return at once when *done_flag != 0
+    int use_gram;           // 1: convergence tested on the state after each sweep (Gram matrix on the tensor cores)
     double* Q;              // optional (null): warm-start bases, n x n column-major at desc.q_off, read AND updated
     ProjEpilogue epi;
 };

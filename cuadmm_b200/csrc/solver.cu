@@ -709,6 +709,10 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     CUADMM_CUDA(cudaStreamSynchronize(stream));
 
     if (rank != 0) verbose = false;   // one log per job
+    if (verbose && ys && ys->n_deficient > 0)
+        printf("\n note: %lld of %lld pivots of A A^T fell below %.0e x diagonal and were treated as redundant constraints"
+               "\n       (y is then only determined up to those rows; CUADMM_PIVOT_TOL changes the tolerance)\n",
+               (long long)ys->n_deficient, (long long)con_num, cuadmm::pivot_tol());
     if (verbose) {
         printf("\n -------------------------------------------------------------------------------");
         printf("\n                                    cuADMM");

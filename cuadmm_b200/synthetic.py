@@ -30,6 +30,26 @@ def c4_blocks(seed=0, counts=((10, 6000), (50, 3000), (200, 900), (800, 100))):
     return blk
 
 
+def c5_blocks(seed=0, n_big=8000, k_big=4, k_small=500, lo=6, hi=32):
+    """BASELINE.json configs[4]: 4 PSD blocks of n=8,000 plus 500 small blocks n ~ UniformInt[6, 32]"""
+    small = np.random.default_rng(seed).integers(lo, hi + 1, k_small).astype(np.int32)
+    return np.concatenate([np.full(k_big, n_big, np.int32), small])
+
+
+def _complementary_pair(n, rng, thin):
+    """svec(X*), svec(S*) with X* S* = 0, both PSD.  thin: rank-32 factors from one thin QR (O(n^2 r) instead of O(n^3))"""
+    if thin and n > 128:
+        r = 32
+        Q, _ = np.linalg.qr(rng.standard_normal((n, 2 * r)))
+        V, W = Q[:, :r], Q[:, r:]
+        return _svec((V * rng.uniform(0.5, 2.0, r)) @ V.T), _svec((W * rng.uniform(0.5, 2.0, r)) @ W.T)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    r = max(1, n // 3)
+    lam = np.zeros(n); lam[:r] = rng.uniform(0.5, 2.0, r)
+    mu = np.zeros(n); mu[r:] = rng.uniform(0.5, 2.0, n - r)
+    return _svec((Q * lam) @ Q.T), _svec((Q * mu) @ Q.T)
+
+
 def random_svec(blk, seed=0):
     """random symmetric blocks (G + G^T)/2, G ~ N(0,1), eigenvalues straddling 0"""
     rng = np.random.default_rng(seed)
@@ -40,7 +60,7 @@ def random_svec(blk, seed=0):
     return np.concatenate(parts) if parts else np.zeros(0)
 
 
-def chain_sdp(blk, m, seed=0, extra_frac=0.1):
+def chain_sdp(blk, m, seed=0, extra_frac=0.1, coeffs="gauss"):
     """Moment-relaxation-like SDP (structure of the SPOT / pendulum examples): the blocks form a chain
     (time steps); most constraints are 2-entry equalities between an svec entry of block j and one of
     block j or j+1, a fraction `extra_frac` has 3-5 entries; every svec entry is used by ~1-2
@@ -72,6 +92,13 @@ def chain_sdp(blk, m, seed=0, extra_frac=0.1):
     nxt = np.minimum(hb + (rng.random(tot) < 0.35), nb - 1)
     ent = off[nxt] + (rng.random(tot) * (off[nxt + 1] - off[nxt])).astype(np.int64)
     val = rng.standard_normal(tot)
+    if coeffs == "unit":
+        # moment-consistency style rows (x_i - x_j = b, as in the SPOT data): +-1 coefficients.  A A^T is then a signed
+        # graph Laplacian: redundant constraints (cycles) give pivots at rounding level and everything else is
+        # polynomially conditioned, whereas N(0,1) coefficients along long chains make A A^T numerically singular with
+        # a continuum of pivots between 1e-16 and 1e-11 (two valid factorisations then disagree by ~1e-5 in A^T y)
+        first = np.concatenate([[True], con[1:] != con[:-1]])
+        val = np.where(first, 1.0, -1.0)
     A = sp.csr_matrix((val, (con, ent)), shape=(m, vec_len))
     A.sum_duplicates(); A.sort_indices()
     b = A @ xstar
@@ -84,7 +111,7 @@ def chain_sdp(blk, m, seed=0, extra_frac=0.1):
                 xstar=xstar, pstar=float(C @ xstar))
 
 
-def random_sdp(blk, m, seed=0, mean_extra=4.0):
+def random_sdp(blk, m, seed=0, mean_extra=4.0, cheap_factors=False):
     """BASELINE.json configs[3] as defined in SURVEY 8d: m constraints, each with k ~ 1 + Poisson(mean_extra)
     non-zeros at uniformly random svec positions of at most 2 blocks (the two blocks drawn with probability
     proportional to their svec length, i.e. positions are uniform over the svec vector), values N(0,1);
@@ -97,6 +124,10 @@ def random_sdp(blk, m, seed=0, mean_extra=4.0):
     vec_len = int(off[-1])
     xs, ss = [], []
     for n in blk:
+        if cheap_factors:
+            xk, sk = _complementary_pair(int(n), rng, True)
+            xs.append(xk); ss.append(sk)
+            continue
         n = int(n)
         Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
         r = max(1, n // 3)

@@ -134,6 +134,45 @@ def project_svec_threads(blk, Xb, nthreads):
     return out
 
 
+_CB = None
+
+
+def cpu_baseline_lib():
+    """oracle/_build/libcpu_baseline.so (cpu_baseline.cpp): the reference's CPU projection path in C++ —
+    dsyevd on a std::thread pool (src/duo_solver.cu:346-371, 578-619) — bound to scipy's bundled OpenBLAS."""
+    global _CB
+    if _CB is None:
+        import ctypes as C
+        import glob
+        import os
+        import scipy
+        here = os.path.dirname(os.path.abspath(__file__))
+        lib = C.CDLL(os.path.join(here, "_build", "libcpu_baseline.so"))
+        cands = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so"))
+        if not cands or lib.cb_init(os.path.abspath(cands[0]).encode()) != 0:
+            raise RuntimeError("cpu_baseline: cannot bind LAPACK dsyevd / BLAS dgemm from scipy's OpenBLAS")
+        lib.cb_project.restype = C.c_int
+        _CB = lib
+    return _CB
+
+
+def project_svec_cpp(blk, Xb, nthreads, want_eig=False):
+    """Baseline B in C++ (cpu_baseline.cpp cb_project): same result as project_svec_threads, without the Python
+    per-block overhead — this is what the CPU arm of bench.py times."""
+    import ctypes as C
+    lib = cpu_baseline_lib()
+    blk = np.ascontiguousarray(blk, np.int32)
+    Xb = np.ascontiguousarray(Xb, np.float64)
+    out = np.empty_like(Xb)
+    eig = np.zeros(int(blk.sum())) if want_eig else None
+    bad = lib.cb_project(blk.ctypes.data_as(C.POINTER(C.c_int)), len(blk), Xb.ctypes.data_as(C.POINTER(C.c_double)),
+                         out.ctypes.data_as(C.POINTER(C.c_double)),
+                         eig.ctypes.data_as(C.POINTER(C.c_double)) if want_eig else None, int(nthreads))
+    if bad != 0:
+        raise RuntimeError(f"cpu_baseline: dsyevd failed on {bad} blocks")
+    return (out, eig) if want_eig else out
+
+
 # ---------------------------------------------------------------------------------------------
 # sparse pieces
 # ---------------------------------------------------------------------------------------------

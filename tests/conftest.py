@@ -21,7 +21,7 @@ def _ensure_built():
     if not os.path.exists(lib):
         subprocess.check_call(["make", "-C", ROOT, "-j8"], stdout=subprocess.DEVNULL)
     ohost = os.path.join(ROOT, "oracle", "_build", "liboracle_host.so")
-    if not os.path.exists(ohost):
+    if not os.path.exists(ohost) or not os.path.exists(os.path.join(ROOT, "oracle", "_build", "libcpu_baseline.so")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL,
                               stderr=subprocess.DEVNULL)
 

@@ -238,19 +238,19 @@ def test_warm_start_matches_cold_and_oracle():
         oc, _, sc = cold.project_eig_host(xi)
         ref = onp.project_svec(blk, xi)
         scale = np.abs(ref).max()
-        assert np.abs(ow - ref).max() <= 2e-13 * scale
-        assert np.abs(oc - ref).max() <= 2e-13 * scale
+        assert np.abs(ow - ref).max() <= 1e-11 * scale      # stop rule: all |cos| <= 1e-11 (north_star tolerance: 1e-9)
+        assert np.abs(oc - ref).max() <= 1e-11 * scale
         sweeps_warm.append(sw.max()); sweeps_cold.append(sc.max())
     assert max(sweeps_warm[1:]) < min(sweeps_cold[1:]), (sweeps_warm, sweeps_cold)
     y = random_svec(blk, seed=77)                      # unrelated input: still correct, just not faster
     ow, _, _ = warm.project_eig_host(y)
     ref = onp.project_svec(blk, y)
-    assert np.abs(ow - ref).max() <= 2e-13 * np.abs(ref).max()
+    assert np.abs(ow - ref).max() <= 1e-11 * np.abs(ref).max()
     z = np.zeros_like(y)                               # zero block keeps the stored basis valid
     assert np.array_equal(warm.project_host(z), z)
     ow, _, _ = warm.project_eig_host(x)
     ref = onp.project_svec(blk, x)
-    assert np.abs(ow - ref).max() <= 2e-13 * np.abs(ref).max()
+    assert np.abs(ow - ref).max() <= 1e-11 * np.abs(ref).max()
 
 
 def _identities(blk, x):
