@@ -319,6 +319,7 @@ _maybe("cuadmm_solver_history", C.c_int, vp, C.c_int, c_f64p, C.c_int64)
 _maybe("cuadmm_solver_times", C.c_int, vp, c_f64p)
 _maybe("cuadmm_solver_launches", C.c_int64, vp)
 _maybe("cuadmm_solver_run_iterations", C.c_int, vp, C.c_int, C.c_int, C.c_int, c_f64p)
+_maybe("cuadmm_solver_run_iterations_ex", C.c_int, vp, C.c_int, C.c_int, c_f64p)
 _maybe("cuadmm_solver_ysolve_stats", C.c_int, vp, c_i64p)
 _maybe("cuadmm_nccl_unique_id", C.c_int, C.c_char_p)
 _maybe("cuadmm_unique_id", C.c_int, C.c_char_p)
@@ -513,6 +514,13 @@ class Solver:
         out = np.zeros(4)
         _check(lib.cuadmm_solver_run_iterations(self.h, int(n), int(sgs), int(profile), _p(out, c_f64p)))
         return dict(total_ms=out[0], projection_ms=out[1], ysolve_ms=out[2], other_ms=out[3])
+
+    def run_iterations_ex(self, n, sgs=True):
+        """profiled pass with the finer stage breakdown (ms totals over the n iterations)"""
+        out = np.zeros(8)
+        _check(lib.cuadmm_solver_run_iterations_ex(self.h, int(n), int(sgs), _p(out, c_f64p)))
+        return dict(total_ms=out[0], projection_ms=out[1], ysolve_ms=out[2], other_ms=out[3], k5_ms=out[4], k8_ms=out[5],
+                    tail_gemv_ms=out[6])
 
     def set_XyS(self, X, y, S, sig):
         X, y, S = _f64(X), _f64(y), _f64(S)

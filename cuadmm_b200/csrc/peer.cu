@@ -244,3 +244,56 @@ void peer_scatter_full_launch(const PeerComm& pc, int64_t nloc, const double* lo
 extern "C" int cuadmm_unique_id(char out[128]) {
     return cuadmm::guarded([&] { CUADMM_REQUIRE(out, "null argument"); cuadmm::make_unique_id(out); });
 }
+
+// ------------------------------------------------------------------------------------------
+// measurement hook (not in the public header): raw cost of the cross-GPU handshakes
+// ------------------------------------------------------------------------------------------
+namespace cuadmm {
+// mode 0: enter + leave per round (what a pushing kernel pays); mode 1: leave only; mode 2: leave only, spin on a
+// volatile load without nanosleep
+__global__ void peer_handshake_probe_kernel(PeerView pv, int rounds, int mode) {
+    for (int i = 0; i < rounds; ++i) {
+        const unsigned long long e = peer_epoch(pv);
+        if (mode == 0) peer_enter(pv, e);
+        if (mode == 2) {
+            __syncthreads();
+            if ((int)threadIdx.x < pv.world) {
+                __threadfence_system();
+                peer_st_release(pv.fin[threadIdx.x] + pv.rank, e);
+                const volatile unsigned long long* f = pv.fin[pv.rank] + threadIdx.x;
+                while (*f < e) { }
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned long long*>(pv.epoch) = e; __threadfence(); }
+            __syncthreads();
+        } else {
+            peer_leave(pv, e);
+            __syncthreads();
+        }
+    }
+}
+}  // namespace cuadmm
+
+extern "C" int cuadmm_debug_peer_handshake(int rank, int world, const char id[128], int device, int rounds, double out_us[3]) {
+    return cuadmm::guarded([&] {
+        cuadmm::PeerComm pc;
+        pc.init(rank, world, id, device, 1 << 16);
+        cudaStream_t st;
+        CUADMM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        cudaEvent_t e0, e1;
+        CUADMM_CUDA(cudaEventCreate(&e0)); CUADMM_CUDA(cudaEventCreate(&e1));
+        for (int mode = 0; mode < 3; ++mode) {
+            cuadmm::peer_handshake_probe_kernel<<<1, 32, 0, st>>>(pc.view(), 10, mode);     // warm-up, aligns the ranks
+            CUADMM_CUDA(cudaEventRecord(e0, st));
+            cuadmm::peer_handshake_probe_kernel<<<1, 32, 0, st>>>(pc.view(), rounds, mode);
+            CUADMM_CUDA(cudaEventRecord(e1, st));
+            CUADMM_CUDA(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            out_us[mode] = 1e3 * ms / rounds;
+        }
+        pc.check(st);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    });
+}

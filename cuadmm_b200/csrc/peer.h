@@ -104,9 +104,13 @@ __device__ __forceinline__ void peer_enter(const PeerView& pv, unsigned long lon
 // all threads of all CTAs, after their last push
 __device__ __forceinline__ void peer_leave(const PeerView& pv, unsigned long long e) {
     __shared__ int s_last;
-    __threadfence_system();
+    // the CTA's remote stores are ordered before thread 0's fence by the barrier (cumulativity): one fence per CTA, and
+    // only at device scope — the system-scope release comes once, from the last CTA, after it has observed all the others
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(pv.cta_count, 1u) == gridDim.x - 1u) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(pv.cta_count, 1u) == gridDim.x - 1u) ? 1 : 0;
+    }
     __syncthreads();
     if (!s_last) return;
     if ((int)threadIdx.x < pv.world) {

@@ -428,8 +428,10 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         CUADMM_CUDA(cudaEventCreate(&ev));
         CUADMM_CUDA(cudaEventRecord(ev, stream));
         prof_ev.push_back(ev);
-        (void)k;
+        prof_tag.push_back(k);
     };
+    ys->prof_ev = prof ? &prof_ev : nullptr;       // the y-solve brackets its dense-tail stage (tags 20 / 21)
+    ys->prof_tag = prof ? &prof_tag : nullptr;
     const int gm_ = ew_grid(con_num, device);
     // K1: rhsy = Rp/sig - A(S-C).  The product asmc = -A(S-C) is kept: in an sGS iteration K5 computes it for
     // the NEW S, which is exactly what K1 of the next iteration needs (S does not change in between), so that
@@ -467,7 +469,9 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
     int n_rd = 0;
     if (iter < switch_admm) {
         // K5-K7: the sGS second half-step
+        mark(6);
         k1(false);
+        mark(7);
         mark(4);
         ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
         mark(5);
@@ -488,6 +492,7 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
         n_rd = nE_blocks;
     }
     // K8  (multi-GPU: partial A_g X_g plus the two local sums of K7 ride one all-reduce)
+    mark(8);
     if (world == 1) {
         e = SpmvEpilogue(); e.mode = 4; e.aux1 = bd.p; e.aux2 = normA.p; e.aux3 = y.p; e.partial = part_rp;
         spmv_launch(*A, 1.0, X.p, 0.0, Rp.p, e, stream); ++launches;
@@ -502,6 +507,8 @@ void cuadmm_solver::enqueue_iteration(int iter, int switch_admm, bool prof) {
             scalar_update_kernel<<<1, 256, 0, stream>>>(st.p, red_buf.p + con_num, 1, part_rp, nE_blocks, hist.p, hist_cap);
         ++launches;
     }
+    mark(9);
+    ys->prof_ev = nullptr; ys->prof_tag = nullptr;
     asmc_valid = iter < switch_admm;     // K5 ran: asmc holds -A(S-C) of the S this iteration ends with
     CUADMM_CUDA(cudaGetLastError());
 }
@@ -581,7 +588,7 @@ void cuadmm_solver::enqueue_half_step() {
     ys->solve(rhsy.p, y.p, stream); launches += ys->launches_per_solve;
 }
 
-void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double out_ms[4]) {
+void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double out_ms[8]) {
     CUADMM_REQUIRE(initialised && hist.n > 0, "run_iterations() needs init() and one solve() first");
     CUADMM_CUDA(cudaSetDevice(device));
     // disable the stop test, keep the reference's sigma cadence running
@@ -598,7 +605,7 @@ void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double 
         if (graph_admm) { cudaGraphExecDestroy(graph_admm); graph_admm = nullptr; }
     }
     for (auto e : prof_ev) cudaEventDestroy(e);
-    prof_ev.clear();
+    prof_ev.clear(); prof_tag.clear();
     cudaEvent_t e0, e1;
     CUADMM_CUDA(cudaEventCreate(&e0)); CUADMM_CUDA(cudaEventCreate(&e1));
     CUADMM_CUDA(cudaEventRecord(e0, stream));
@@ -607,19 +614,27 @@ void cuadmm_solver::run_iterations(int n_iters, bool sgs, bool profile_, double 
     CUADMM_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    out_ms[0] = ms; out_ms[1] = out_ms[2] = out_ms[3] = 0.0;
+    out_ms[0] = ms;
+    for (int k = 1; k < 8; ++k) out_ms[k] = 0.0;
     if (profile_) {
-        for (size_t i = 0; i + 5 < prof_ev.size(); i += 6) {
-            float a = 0, b = 0, c = 0;
-            cudaEventElapsedTime(&a, prof_ev[i], prof_ev[i + 1]);
-            cudaEventElapsedTime(&b, prof_ev[i + 2], prof_ev[i + 3]);
-            cudaEventElapsedTime(&c, prof_ev[i + 4], prof_ev[i + 5]);
-            out_ms[2] += a + (sgs ? c : 0.f);
-            out_ms[1] += b;
-        }
+        // intervals between an event tagged `a` and the next one tagged `b`
+        auto span = [&](int a, int b) {
+            double tot = 0.0;
+            for (size_t i = 0; i < prof_ev.size(); ++i) {
+                if (prof_tag[i] != a) continue;
+                for (size_t j = i + 1; j < prof_ev.size(); ++j)
+                    if (prof_tag[j] == b) { float t = 0.f; cudaEventElapsedTime(&t, prof_ev[i], prof_ev[j]); tot += t; break; }
+            }
+            return tot;
+        };
+        out_ms[1] = span(2, 3);
+        out_ms[2] = span(0, 1) + (sgs ? span(4, 5) : 0.0);
         out_ms[3] = out_ms[0] - out_ms[1] - out_ms[2];
+        out_ms[4] = span(6, 7);       // K5: A (S - C) (+ reduction over ranks) + rhsy
+        out_ms[5] = span(8, 9);       // K8: A X (+ reduction over ranks) + scalar update
+        out_ms[6] = span(20, 21);     // dense-tail GEMVs of all y-solves
         for (auto e : prof_ev) cudaEventDestroy(e);
-        prof_ev.clear();
+        prof_ev.clear(); prof_tag.clear();
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     h_st->done = 1;
@@ -908,7 +923,15 @@ int64_t cuadmm_solver_launches(const cuadmm_solver_t* s) { return s ? s->launche
 int cuadmm_solver_run_iterations(cuadmm_solver_t* s, int n_iters, int sgs, int profile, double out_ms[4]) {
     return guarded([&] {
         CUADMM_REQUIRE(s && out_ms && n_iters >= 0, "bad argument");
-        s->run_iterations(n_iters, sgs != 0, profile != 0, out_ms);
+        double t[8];
+        s->run_iterations(n_iters, sgs != 0, profile != 0, t);
+        for (int k = 0; k < 4; ++k) out_ms[k] = t[k];
+    });
+}
+int cuadmm_solver_run_iterations_ex(cuadmm_solver_t* s, int n_iters, int sgs, double out_ms[8]) {
+    return guarded([&] {
+        CUADMM_REQUIRE(s && out_ms && n_iters >= 0, "bad argument");
+        s->run_iterations(n_iters, sgs != 0, true, out_ms);
     });
 }
 

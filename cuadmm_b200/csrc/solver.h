@@ -82,6 +82,7 @@ struct cuadmm_solver {
     int nA_blocks = 0, nAt_blocks = 0, nE_blocks = 0;
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_tag;
 
     ~cuadmm_solver();
     void init(int eig_stream_num_per_gpu, int cpu_eig_thread_num, int64_t vec_len, int64_t con_num,
@@ -92,7 +93,7 @@ struct cuadmm_solver {
     void solve(int max_iter, double stop_tol, int sig_update_threshold, int sig_update_stage_1,
                int sig_update_stage_2, int switch_admm, double sigscale, bool if_first);
     void enqueue_iteration(int iter, int switch_admm, bool prof = false);
-    void run_iterations(int n_iters, bool sgs, bool profile, double out_ms[4]);
+    void run_iterations(int n_iters, bool sgs, bool profile, double out_ms[8]);
     void enqueue_half_step();
     // whole-iteration CUDA graphs (one for the sGS iteration, one for the plain ADMM iteration)
     cudaGraphExec_t graph_sgs = nullptr, graph_admm = nullptr;

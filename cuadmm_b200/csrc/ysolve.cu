@@ -365,10 +365,16 @@ __global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t
 // are read (tile_ptr / tile_col: per tile row, runs of consecutive non-empty tiles as column
 // ranges): the inverse of the trailing factor block inherits
 // the block structure of the separators it came from and is often half empty.
+// One CTA = 8 consecutive rows x all their columns: warp w takes the 64-column chunks c == w (mod 8) of the tile row's
+// runs for ALL 8 rows (8 independent accumulators, the input chunk loaded once for the 8 rows), then the 8 x 8 partials
+// are reduced through shared memory.  A single row of 10k columns used to be one warp's dependent chain of ~160 loads
+// (~30 us however few rows the launch had — which is why splitting the rows over ranks bought nothing); now the longest
+// chain is 1/8 of that and every step has 9 loads in flight per lane.
 // Sharded solver (npush > 0): this rank computes rows [row0, row0 + nrows) only and stores each result into every
-// rank's copy of `out` (and of the scattered y) over peer memory; the kernel ends with the peer_leave handshake, so
-// when it retires every rank holds the complete vector.  No peer_enter is needed: a peer can only reach this
-// kernel after the handshake of the previous one, which this rank joined after its last read of the buffers.
+// rank's copy of `out` over peer memory (one coalesced 64-byte store per CTA and peer); the kernel ends with the
+// peer_leave handshake, so when it retires every rank holds the complete vector.  No peer_enter is needed: a peer
+// can only reach this kernel after the handshake of the previous one, which this rank joined after its last read of
+// the buffers.  row0 is a multiple of 8, so the 8 rows of a CTA share one 64-row tile row (= one list of column runs).
 __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double* __restrict__ T, const double* in,
                                                         double* out, const int32_t* __restrict__ tile_ptr,
                                                         const int32_t* __restrict__ tile_col, double* out_scatter,
@@ -377,57 +383,95 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
                                                         int64_t row0, int64_t nrows, int npush, PeerView pv,
                                                         PeerPtrs outp, PeerPtrs scatp) {
     if (done_flag && *done_flag) return;
-    const int lane = threadIdx.x & 31;
+    __shared__ double part[8][9];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned long long ep = 0;
     if (npush) ep = peer_epoch(pv);
     // the CTAs with the longest rows go first (lower-triangular storage: the last rows), so the grid's tail
     // wave is made of short rows
     const int64_t cta = longest_last ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
-    const int64_t lrow = cta * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (lrow >= nrows) {
-        if (npush) peer_leave(pv, ep);
-        return;
-    }
-    const int64_t row = row0 + lrow;
-    const double* Ti = T + row * r;
-    const int I = (int)(row >> 6);
-    double acc0 = 0.0, acc1 = 0.0;
-    const bool vec = (r & 1) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0;   // rows 16-byte aligned (tile columns are multiples of 64)
-    const bool in_al = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    for (int t = tile_ptr[I]; t < tile_ptr[I + 1]; ++t) {      // runs of consecutive non-empty tiles: [first, last) columns
-        const int64_t j0 = tile_col[2 * t];
-        const int64_t j1 = min((int64_t)tile_col[2 * t + 1], r);
-        if (vec) {
-            const int64_t jv = j0 + ((j1 - j0) & ~(int64_t)1);
-#pragma unroll 4
-            for (int64_t j = j0 + 2 * lane; j < jv; j += 64) {
-                const double2 a = __ldcs(reinterpret_cast<const double2*>(Ti + j));   // streamed once: evict first
-                const double2 b = in_al ? *reinterpret_cast<const double2*>(in + j) : make_double2(in[j], in[j + 1]);
-                acc0 = fma(a.x, b.x, acc0);
-                acc1 = fma(a.y, b.y, acc1);
+    const int64_t base = row0 + cta * 8;
+    const int nr = (int)max((int64_t)0, min((int64_t)8, row0 + nrows - base));     // rows of this CTA
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    if (nr > 0) {
+        const int I = (int)(base >> 6);
+        const bool vec = (r & 1) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+        const double* Tb = T + base * r;
+        int g = 0;                                        // running chunk index over the runs of this tile row
+        for (int t = tile_ptr[I]; t < tile_ptr[I + 1]; ++t) {
+            const int64_t j0 = tile_col[2 * t];
+            const int64_t j1 = min((int64_t)tile_col[2 * t + 1], r);
+            const int nch = (int)((j1 - j0 + 63) >> 6);
+            // first chunk of this run that belongs to warp w
+            int c = (w - (g & 7)) & 7;
+            g += nch;
+            for (; c < nch; c += 8) {
+                const int64_t j = j0 + ((int64_t)c << 6) + 2 * lane;
+                if (vec) {
+                    if (j + 1 < j1) {
+                        const double2 b = *reinterpret_cast<const double2*>(in + j);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (q < nr) {
+                                const double2 a = __ldcs(reinterpret_cast<const double2*>(Tb + q * r + j));   // streamed once
+                                acc[q] = fma(a.x, b.x, fma(a.y, b.y, acc[q]));
+                            }
+                        }
+                    } else if (j < j1) {
+                        const double b = in[j];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (q < nr) acc[q] = fma(Tb[q * r + j], b, acc[q]);
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int64_t jj = j0 + ((int64_t)c << 6) + lane + 32 * h;
+                        if (jj < j1) {
+                            const double b = in[jj];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) if (q < nr) acc[q] = fma(Tb[q * r + jj], b, acc[q]);
+                        }
+                    }
+                }
             }
-            if (lane == 0 && jv < j1) acc0 = fma(Ti[jv], in[jv], acc0);
-        } else {
-#pragma unroll 4
-            for (int64_t j = j0 + lane; j < j1; j += 32) acc0 = fma(Ti[j], in[j], acc0);
         }
     }
-    double acc = acc0 + acc1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
     if (lane == 0) {
-        if (npush == 0) {
-            out[row] = acc;
-            if (out_scatter) out_scatter[out_perm[perm_base + row]] = acc;
-        } else {
-            for (int q = 0; q < npush; ++q) outp.p[q][row] = acc;
-            if (out_scatter) {
-                const int32_t d = out_perm[perm_base + row];
-                for (int q = 0; q < npush; ++q) scatp.p[q][d] = acc;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) part[w][q] = acc[q];
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < 8 * max(npush, 1)) {
+        const int q = t >> 3, rr = t & 7;
+        if (rr < nr) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += part[k][rr];          // fixed order: identical on every rank
+            if (npush == 0) {
+                out[base + rr] = v;
+                if (out_scatter) out_scatter[out_perm[perm_base + base + rr]] = v;
+            } else {
+                outp.p[q][base + rr] = v;
             }
         }
     }
     if (npush) peer_leave(pv, ep);
+}
+
+// y[perm[base + i]] = x_tail[i]: the scatter of the dense-tail solution into y (sharded solver; local)
+__global__ void __launch_bounds__(256) tail_scatter_kernel(int64_t r, const double* __restrict__ xt, const int32_t* __restrict__ perm,
+                                                           int64_t base, double* y, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < r) y[perm[base + i]] = xt[i];
 }
 
 // gather/external fold, then the packed CTA-per-subtree kernel on `st` and the warp-per-subtree kernel
@@ -1100,6 +1144,11 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
     CUADMM_CUDA(cudaEventCreateWithFlags(&Y->streams.fork, cudaEventDisableTiming));
     CUADMM_CUDA(cudaEventCreateWithFlags(&Y->streams.join, cudaEventDisableTiming));
     Y->alg_bytes = 2 * (12 * Y->nnz_L + 8 * m) + 24 * m;
+    if (const char* e = getenv("CUADMM_TAIL_SIM_WORLD")) {
+        Y->sim_world = atoi(e);
+        const char* r = getenv("CUADMM_TAIL_SIM_RANK");
+        if (Y->sim_world > 1 && n_tail > 0) Y->split_tail_rows(Y->sim_world, r ? atoi(r) : 0);
+    }
     CUADMM_CUDA(cudaDeviceSynchronize());
     return Y.release();
 }
@@ -1120,20 +1169,25 @@ void cuadmm_ysolve_s::enable_peer(const PeerComm* pc, size_t off_tmp, size_t off
     peer_x = pc->ptrs(off_x);
     tail_tmp_p = pc->local<double>(off_tmp);
     x_p = pc->local<double>(off_x);
-    // rows of each tail GEMV split into `world` contiguous ranges of equal work (columns read)
+    if (n_tail > 0 && pc->world > 1) launches_per_solve += 1;     // tail_scatter_kernel
+    split_tail_rows(pc->world, pc->rank);
+}
+
+// rows of each tail GEMV split into `world` contiguous ranges of equal work (columns read)
+void cuadmm_ysolve_s::split_tail_rows(int world, int rank) {
     for (int k = 0; k < 2; ++k) {
         const std::vector<double>& c = h_tail_cost[k];
         double total = 0.0;
         for (int64_t i = 0; i < n_tail; ++i) total += c[i >> 6] + 32.0;
-        std::vector<int64_t> cut(pc->world + 1, n_tail);
+        std::vector<int64_t> cut(world + 1, n_tail);
         cut[0] = 0;
         double acc = 0.0;
         int q = 1;
-        for (int64_t i = 0; i < n_tail && q < pc->world; ++i) {
+        for (int64_t i = 0; i < n_tail && q < world; ++i) {
             acc += c[i >> 6] + 32.0;
-            while (q < pc->world && acc >= total * q / pc->world) cut[q++] = i + 1;
+            while (q < world && acc >= total * q / world) cut[q++] = std::min<int64_t>(n_tail, (i + 1 + 7) / 8 * 8);   // CTA = 8 rows
         }
-        tail_row0[k] = cut[pc->rank]; tail_row1[k] = cut[pc->rank + 1];
+        tail_row0[k] = cut[rank]; tail_row1[k] = cut[rank + 1];
     }
 }
 
@@ -1143,20 +1197,31 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
     double* tmpv = tail_tmp_p ? tail_tmp_p : tail_tmp.p;
     // forward: z = L11^-1 P rhs (lead), z_tail = P rhs - L21 z_lead
     launch_sweep(fwd, d_rhs_, perm.p, z.p, nullptr, nullptr, done_flag, st, streams);
+    auto mark = [&](int tag) {
+        if (!prof_ev) return;
+        cudaEvent_t ev;
+        CUADMM_CUDA(cudaEventCreate(&ev));
+        CUADMM_CUDA(cudaEventRecord(ev, st));
+        prof_ev->push_back(ev); prof_tag->push_back(tag);
+    };
     if (n_tail > 0) {
+        mark(20);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
-        if (!peer || peer->world == 1) {
+        if (sim_world > 1 && !peer) {
+            // measurement only (CUADMM_TAIL_SIM_WORLD=W, CUADMM_TAIL_SIM_RANK=r): the rows rank r of W would compute,
+            // no exchange — the result is incomplete, the timing is that of one rank's share
+            const int64_t n0 = tail_row1[0] - tail_row0[0], n1 = tail_row1[1] - tail_row0[1];
+            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n0 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p,
+                tail_tcol.p, nullptr, nullptr, 0, done_flag, 1, tail_row0[0], n0, 0, PeerView(), PeerPtrs(), PeerPtrs());
+            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n1 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p,
+                tail_tcol_t.p, d_y_, perm.p, n_lead, done_flag, 0, tail_row0[1], n1, 0, PeerView(), PeerPtrs(), PeerPtrs());
+        } else if (!peer || peer->world == 1) {
             const int blocks = (int)((n_tail + 7) / 8);
             tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p, tail_tcol.p,
                                                      nullptr, nullptr, 0, done_flag, 1, 0, n_tail, 0, PeerView(), PeerPtrs(), PeerPtrs());
             tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p, tail_tcol_t.p,
                                                      d_y_, perm.p, n_lead, done_flag, 0, 0, n_tail, 0, PeerView(), PeerPtrs(), PeerPtrs());
         } else {
-            // y must live in the peer arena: the same offset in every rank's arena
-            const char* yb = reinterpret_cast<const char*>(d_y_);
-            const char* lb = peer->base[peer->rank];
-            CUADMM_REQUIRE(yb >= lb && yb + sizeof(double) * m <= lb + peer->bytes, "sharded y-solve: y is not in the peer arena");
-            const PeerPtrs py = peer->ptrs((size_t)(yb - lb));
             PeerPtrs pxt = peer_x;
             for (int q = 0; q < peer->world; ++q) pxt.p[q] += n_lead;
             const PeerView pv = peer->view();
@@ -1164,9 +1229,11 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
             tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n0 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p,
                 tail_tcol.p, nullptr, nullptr, 0, done_flag, 1, tail_row0[0], n0, peer->world, pv, peer_tmp, PeerPtrs());
             tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n1 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p,
-                tail_tcol_t.p, d_y_, perm.p, n_lead, done_flag, 0, tail_row0[1], n1, peer->world, pv, pxt, py);
+                tail_tcol_t.p, nullptr, nullptr, 0, done_flag, 0, tail_row0[1], n1, peer->world, pv, pxt, PeerPtrs());
+            tail_scatter_kernel<<<(int)((n_tail + 255) / 256), 256, 0, st>>>(n_tail, xv + n_lead, perm.p, n_lead, d_y_, done_flag);
         }
         CUADMM_CUDA(cudaGetLastError());
+        mark(21);
     }
     // backward: x_lead = L11^-T (z_lead - L21^T x_tail), scattered into y
     launch_sweep(bwd, z.p, nullptr, xv, d_y_, perm.p, done_flag, st, streams);

@@ -75,7 +75,11 @@ struct cuadmm_ysolve_s {
     int64_t tail_row0[2] = {0, 0}, tail_row1[2] = {0, 0};   // this rank's rows of L22^-1 / L22^-T
     std::vector<double> h_tail_cost[2]; // per 64-row tile row: columns read (work per row)
     void enable_peer(const cuadmm::PeerComm* pc, size_t off_tmp, size_t off_x);
+    void split_tail_rows(int world, int rank);
+    int sim_world = 0;                  // measurement only: CUADMM_TAIL_SIM_WORLD
     const int* done_flag = nullptr;
+    std::vector<cudaEvent_t>* prof_ev = nullptr;   // profiling (solver): events around the dense-tail stage, tags 20 / 21
+    std::vector<int>* prof_tag = nullptr;
     cuadmm::SweepStreams streams;
     ~cuadmm_ysolve_s();
     int launches_per_solve = 0;

@@ -188,6 +188,9 @@ int64_t cuadmm_solver_launches(const cuadmm_solver_t* s);
  * out_ms[2] = both y-solves (:487-500,704-717), out_ms[3] = everything else (SpMVs + scalar kernel).
  * Requires solve() to have been called once (it sets the run parameters). */
 int  cuadmm_solver_run_iterations(cuadmm_solver_t* s, int n_iters, int sgs, int profile, double out_ms[4]);
+/* same with the finer breakdown (always profiled): out_ms[0..3] as above, out_ms[4] = K5 (A (S-C), its reduction over
+ * ranks, rhsy), out_ms[5] = K8 (A X, its reduction over ranks, scalar update), out_ms[6] = dense-tail GEMVs of all y-solves */
+int  cuadmm_solver_run_iterations_ex(cuadmm_solver_t* s, int n_iters, int sgs, double out_ms[8]);
 /* y-solve statistics of the solver's factorisation (see cuadmm_ysolve_stats) */
 int  cuadmm_solver_ysolve_stats(const cuadmm_solver_t* s, int64_t out[8]);
 
