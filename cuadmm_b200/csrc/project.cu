@@ -172,8 +172,11 @@ __device__ __forceinline__ bool jacobi_gram_converged(const double* G, const dou
     return !any;
 }
 
+// resident CTAs per SM the register allocation must allow (the sweeps are throughput-bound at full batches)
+constexpr int jacobi_min_ctas(int T) { return T <= 64 ? 8 : T <= 128 ? 4 : T <= 256 ? 2 : 1; }
+
 template <int T, int L, int RPL, bool WARP>
-__global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
+__global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(ProjArgs a, int nmax) {
     extern __shared__ double smem[];
     constexpr int NT = WARP ? 32 : T;
     constexpr int NG = NT / L;
@@ -198,15 +201,25 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     double* __restrict__ xout = a.Xproj + d.svec_off;
 
     // ---- svec -> smat (vector_to_matrices); max |entry| for an exact power-of-two prescale ----
+    // (eight loads in flight per thread: with one block per SM — a rank's share on 8 GPUs — the stage is bound by the
+    // latency of ONE block, and a loop of dependent-looking global loads was ~17 DRAM round trips of it)
     double amax = 0.0;
-    for (int idx = tid; idx < ntri; idx += NT) {
-        int r, c;
-        tri_unrank(idx, r, c);
-        const double v = xin[idx];
-        amax = fmax(amax, fabs(v));          // fmax drops NaN; caught below through the norm
-        const double v2 = (r == c) ? v : v * CUADMM_SQRT2INV;
-        G[r + c * ld] = v2;
-        G[c + r * ld] = v2;
+    for (int idx0 = tid; idx0 < ntri; idx0 += NT * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int idx = idx0 + u * NT; v[u] = (idx < ntri) ? __ldg(xin + idx) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * NT;
+            if (idx < ntri) {
+                int r, c;
+                tri_unrank(idx, r, c);
+                amax = fmax(amax, fabs(v[u]));          // fmax drops NaN; caught below through the norm
+                const double v2 = (r == c) ? v[u] : v[u] * CUADMM_SQRT2INV;
+                G[r + c * ld] = v2;
+                G[c + r * ld] = v2;
+            }
+        }
     }
     amax = mat_max<NT, WARP>(amax, red, tid);
     int ex = 0;
@@ -278,35 +291,40 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
                 af[kk] = (kk < nk && row < n && k < n) ? G[row + k * ld] : 0.0;
             }
             __syncwarp();                                   // the whole strip is in registers before any of it is overwritten
-            for (int j0 = 0; j0 < n; j0 += 32) {            // four 8-column tiles at a time: independent accumulators
-                const double* __restrict__ qc[4];
-                bool cv[4];
-                double c[4][2];
+            for (int j0 = 0; j0 < n; j0 += 16) {
+                // two 8-column tiles per pass; ALL k-fragments of both tiles are requested from L2 before the first mma
+                // (2 x KF loads in flight per lane) — issued one k-step at a time, every step paid an L2 round trip
+                constexpr int KC = KF < 16 ? KF : 16;          // k-fragments requested per batch (register budget)
+                const int col0 = j0 + fr, col1 = j0 + 8 + fr;
+                const double* __restrict__ q0 = Qb + (size_t)min(col0, n - 1) * n;
+                const double* __restrict__ q1 = Qb + (size_t)min(col1, n - 1) * n;
+                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int col = j0 + 8 * u + fr;
-                    cv[u] = col < n;
-                    qc[u] = Qb + (size_t)min(col, n - 1) * n;
-                    c[u][0] = 0.0; c[u][1] = 0.0;
-                }
+                for (int kb = 0; kb < KF; kb += KC) {
+                    if (kb < nk) {
+                        double b0[KC], b1[KC];
 #pragma unroll
-                for (int kk = 0; kk < KF; ++kk) {
-                    if (kk < nk) {
-                        const int k = kk * 4 + fk;
-                        double bv[4];
+                        for (int kk = 0; kk < KC; ++kk) {
+                            const int k = (kb + kk) * 4 + fk;
+                            const bool kv = kb + kk < nk && k < n;
+                            b0[kk] = (kv && col0 < n) ? __ldg(q0 + k) : 0.0;
+                            b1[kk] = (kv && col1 < n) ? __ldg(q1 + k) : 0.0;
+                        }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) bv[u] = (cv[u] && k < n) ? __ldg(qc[u] + k) : 0.0;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) jacobi_dmma(c[u][0], c[u][1], af[kk], bv[u]);
+                        for (int kk = 0; kk < KC; ++kk) {
+                            if (kb + kk < KF && kb + kk < nk) {
+                                jacobi_dmma(c00, c01, af[kb + kk], b0[kk]);
+                                jacobi_dmma(c10, c11, af[kb + kk], b1[kk]);
+                            }
+                        }
                     }
                 }
                 if (row < n) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int cc = j0 + 8 * u + 2 * fk;
-                        if (cc < n) G[row + cc * ld] = c[u][0];
-                        if (cc + 1 < n) G[row + (cc + 1) * ld] = c[u][1];
-                    }
+                    const int cc = j0 + 2 * fk;
+                    if (cc < n) G[row + cc * ld] = c00;
+                    if (cc + 1 < n) G[row + (cc + 1) * ld] = c01;
+                    if (cc + 8 < n) G[row + (cc + 8) * ld] = c10;
+                    if (cc + 9 < n) G[row + (cc + 9) * ld] = c11;
                 }
             }
         }
@@ -472,22 +490,43 @@ __global__ void __launch_bounds__(T) proj_jacobi_kernel(ProjArgs a, int nmax) {
     // ---- rebuild + smat -> svec (matrices_to_vector), optional fused S / SmC ----
     double sig = 1.0;
     if (a.epi.X) sig = *a.epi.sig_ptr;
-    for (int idx = tid; idx < ntri; idx += NT) {
-        int r, c;
-        tri_unrank(idx, r, c);
-        double acc = 0.0;
+    for (int idx0 = tid; idx0 < ntri; idx0 += NT * 2) {
+        // two entries per pass; the epilogue's global operands are requested before the accumulation they do not depend on
+        const int idx1 = idx0 + NT;
+        const bool two = idx1 < ntri;
+        double xv0 = 0.0, rd0 = 0.0, cd0 = 0.0, xv1 = 0.0, rd1 = 0.0, cd1 = 0.0;
+        if (a.epi.X) {
+            const int64_t g0 = d.svec_off + idx0;
+            xv0 = __ldg(a.epi.X + g0); rd0 = __ldg(a.epi.Rd1 + g0); cd0 = __ldg(a.epi.Cd + g0);
+            if (two) { const int64_t g1 = d.svec_off + idx1; xv1 = __ldg(a.epi.X + g1); rd1 = __ldg(a.epi.Rd1 + g1); cd1 = __ldg(a.epi.Cd + g1); }
+        }
+        int r0, c0, r1 = 0, c1 = 0;
+        tri_unrank(idx0, r0, c0);
+        if (two) tri_unrank(idx1, r1, c1);
+        double acc0 = 0.0, acc1 = 0.0;
         for (int jj = 0; jj < kpos; ++jj) {
             const double* Gj = G + pos[jj] * ld;
-            acc = fma(Gj[r], Gj[c], acc);
+            acc0 = fma(Gj[r0], Gj[c0], acc0);
+            acc1 = fma(Gj[r1], Gj[c1], acc1);
         }
-        acc *= s_true;
-        const double out = (r == c) ? acc : acc * CUADMM_SQRT2;
-        xout[idx] = out;
+        acc0 *= s_true; acc1 *= s_true;
+        const double out0 = (r0 == c0) ? acc0 : acc0 * CUADMM_SQRT2;
+        xout[idx0] = out0;
         if (a.epi.X) {
-            const int64_t gi = d.svec_off + idx;
-            const double Sv = (out - a.epi.X[gi]) / sig - a.epi.Rd1[gi];
-            a.epi.S[gi] = Sv;
-            a.epi.SmC[gi] = Sv - a.epi.Cd[gi];
+            const int64_t g0 = d.svec_off + idx0;
+            const double Sv = (out0 - xv0) / sig - rd0;
+            a.epi.S[g0] = Sv;
+            a.epi.SmC[g0] = Sv - cd0;
+        }
+        if (two) {
+            const double out1 = (r1 == c1) ? acc1 : acc1 * CUADMM_SQRT2;
+            xout[idx1] = out1;
+            if (a.epi.X) {
+                const int64_t g1 = d.svec_off + idx1;
+                const double Sv = (out1 - xv1) / sig - rd1;
+                a.epi.S[g1] = Sv;
+                a.epi.SmC[g1] = Sv - cd1;
+            }
         }
     }
 }

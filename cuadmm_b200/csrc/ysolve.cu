@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t*
 // Packed subtrees.  The x-independent data of a subtree (structure + values of its rows, already in
 // level order) is laid out on the host as a stream of fixed-size CHUNKS, which one thread moves
 // global -> shared with 1-D TMA bulk copies (cp.async.bulk + mbarrier) kPkRing chunks ahead of the
-// warps that consume them.  The unknowns live in shared memory for the whole kernel, so a level
+// warps that consume them.  Chunk size (measured on the bench problem, ms per solve): 8 KB x 6: 0.378, 16 KB x 4:
+// 0.331, 32 KB x 3: 0.310, 48 KB x 3: 0.301, 64 KB x 2: 0.295 — every chunk boundary is a barrier on top of the
+// level barriers, so the largest chunk that leaves room for the unknowns wins.  The unknowns live in shared memory for the whole kernel, so a level
 // costs one __syncthreads plus shared-memory traffic: no global load sits on the critical path.
 //
 // chunk:  u16 nseg, u16 nslots, u16 seg_end[nseg], u16 rec_off[nslots] (8-byte units), records...
@@ -162,8 +164,14 @@ __global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t*
 //         (8 short rows x 4 lanes, or one long row x 32 lanes; idx = shared-memory index of the dependency)
 // Dependencies OUTSIDE the subtree are final when the kernel starts; the prologue folds them into
 // the right-hand side:  xs[loc] = rhs[u] - sum_ext val * x[dep].
-static constexpr int kPkChunk = 16384;
-static constexpr int kPkRing = 4;
+#ifndef CUADMM_PK_CHUNK
+#define CUADMM_PK_CHUNK 65536
+#endif
+#ifndef CUADMM_PK_RING
+#define CUADMM_PK_RING 2
+#endif
+static constexpr int kPkChunk = CUADMM_PK_CHUNK;
+static constexpr int kPkRing = CUADMM_PK_RING;
 static constexpr int kPkThreads = 1024;
 static constexpr int kPkRecHeader = 8 + 32 + 16 + 16 + 16 + 64;
 static constexpr int kPkMaxRowEntries = 768;
@@ -964,10 +972,11 @@ static void upload_sweep(const HostSweep& H, TriSweep& S) {
 static int64_t choose_subtrees(const CholFactor& F, int64_t n_lead, std::vector<int32_t>& sub) {
     const int64_t n = F.n;
     sub.assign(n, -1);
-    int64_t cap = 12288;          // rows per subtree: its unknowns live in shared memory (96 KB + the chunk ring)
+    int64_t cap = 12000;          // rows per subtree: its unknowns (+ up to 384 chain slots) live in shared memory next to the
+                                  // 2 x 64 KB chunk ring: (12000 + 384) * 8 + 131136 bytes <= 227 KB
     if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_CAP")) cap = atoll(e);
     if (cap <= 0) return 0;
-    cap = std::min<int64_t>(cap, 28000);   // 227 KB of shared memory
+    cap = std::min<int64_t>(cap, (int64_t)(232448 - kPkRing * kPkChunk - 64) / 8 - kPkChainMax);   // 227 KB of shared memory
     int64_t min_size = 2;         // (measured: peeling small subtrees off into extra top levels costs more than their CTAs)
     if (const char* e = getenv("CUADMM_SWEEP_SUBTREE_MIN")) min_size = atoll(e);
     std::vector<int64_t> size(n, 1);

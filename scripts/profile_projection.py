@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import torch
 import cuadmm_b200 as cu
 from cuadmm_b200.synthetic import c2b_blocks, random_svec
-blk = c2b_blocks(2000, 6, 60, 0)
+blk = c2b_blocks(2000, 6, 60, 0)[:int(os.environ.get("NB", "2000"))]
 drift = float(os.environ.get("DRIFT", "1e-4")); warm = int(os.environ.get("WARM", "3"))
 x = random_svec(blk, seed=0); d = random_svec(blk, seed=1)
 p = cu.Plan(blk, device=0)
