@@ -26,6 +26,7 @@ void spmv_set_done_flag(cuadmm_spmv_s& A, const int* flag);
 // small kernels
 // ------------------------------------------------------------------------------------------
 static constexpr int kEwThreads = 256;
+static constexpr int64_t kHistRing = 4096;      // device history ring (entries per array)
 
 // ADMM branch of step 4 (no second y-solve): Rd = Rd1 + S ; X += tau*sig*Rd ; partial sums
 __global__ void __launch_bounds__(kEwThreads) x_update_kernel(int64_t n, const double* __restrict__ Rd1,
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(256) scalar_update_kernel(DevState* st, const 
     st->sig = sig;
     st->errRp = errRp; st->errRd = errRd; st->pobj = pobj; st->dobj = dobj;
     st->maxfeas = maxfeas; st->relgap = relgap; st->feasratio = feasratio;
-    if (iter - 1 < hist_cap) {
-        const int64_t k = iter - 1;
+    {
+        const int64_t k = (int64_t)(iter - 1) % hist_cap;      // ring: the host drains it at every log boundary
         hist[0 * hist_cap + k] = pobj;  hist[1 * hist_cap + k] = dobj;
         hist[2 * hist_cap + k] = errRp; hist[3 * hist_cap + k] = errRd;
         hist[4 * hist_cap + k] = relgap; hist[5 * hist_cap + k] = sig;
@@ -676,14 +677,37 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     if (X_best.n < std::max<int64_t>(n, 1)) {   // always allocated: the ADMM graph bakes these pointers
         X_best.alloc(std::max<int64_t>(n, 1)); y_best.alloc(std::max<int64_t>(m, 1)); S_best.alloc(std::max<int64_t>(n, 1));
     }
-    if ((int64_t)max_iter + 1 > hist_cap || hist.n == 0) {   // keep the buffer across warm-restart calls
-        hist_cap = (int64_t)max_iter + 1;
+    if (hist.n == 0) {
+        // history ring on the device (the reference keeps max_iter + 1 entries per array: 64 MB for main.cu's 1e6);
+        // drained into host vectors whenever the loop below synchronises (every <= 100 iterations)
+        hist_cap = kHistRing;
         hist.alloc(8 * hist_cap);
         // the captured graphs bake the history pointer
         if (graph_sgs) { cudaGraphExecDestroy(graph_sgs); graph_sgs = nullptr; }
         if (graph_admm) { cudaGraphExecDestroy(graph_admm); graph_admm = nullptr; }
     }
     info_iter_num = 0;
+    for (auto& v : h_hist) v.clear();
+    int64_t drained = 0;                 // iterations whose history entries are already on the host
+    auto drain = [&](int64_t upto) {     // entries [drained, upto) of the ring -> host (stream must be idle afterwards)
+        if (upto <= drained) return;
+        CUADMM_REQUIRE(upto - drained <= hist_cap, "internal: history ring overrun");
+        const int64_t n0 = upto - drained;
+        for (int q = 0; q < 8; ++q) {
+            const size_t base = h_hist[q].size();
+            h_hist[q].resize(base + (size_t)n0);
+            int64_t done_ = 0;
+            while (done_ < n0) {
+                const int64_t k = (drained + done_) % hist_cap;
+                const int64_t len = std::min(n0 - done_, hist_cap - k);
+                CUADMM_CUDA(cudaMemcpyAsync(h_hist[q].data() + base + done_, hist.p + q * hist_cap + k, sizeof(double) * len,
+                                            cudaMemcpyDeviceToHost, stream));
+                done_ += len;
+            }
+        }
+        CUADMM_CUDA(cudaStreamSynchronize(stream));
+        drained = upto;
+    };
     asmc_valid = false;                  // X, y, S may have been replaced / rescaled since the last call
 
     // state for this call
@@ -744,6 +768,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
         CUADMM_CUDA(cudaStreamSynchronize(stream));
         const bool done = h_st->done != 0;
         const int cur = h_st->iter;
+        drain((int64_t)cur - 1);
         if (verbose && (done || is_log_iter(cur))) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev_start, ev_now);
@@ -778,10 +803,7 @@ void cuadmm_solver::solve(int max_iter, double stop_tol, int sig_update_threshol
     scale_vec_kernel<<<gm, 256, 0, stream>>>(m, y.p, normA.p, Cscale, 1);
     scale_kernel<<<gv, 256, 0, stream>>>(n, S.p, Cscale);
     launches += 3;
-    h_hist.assign(8 * (size_t)std::max<int64_t>(info_iter_num, 0), 0.0);
-    for (int q = 0; q < 8 && info_iter_num > 0; ++q)
-        CUADMM_CUDA(cudaMemcpyAsync(h_hist.data() + q * info_iter_num, hist.p + q * hist_cap, sizeof(double) * info_iter_num,
-                                    cudaMemcpyDeviceToHost, stream));
+    drain(info_iter_num);
     CUADMM_CUDA(cudaEventRecord(ev_now, stream));
     CUADMM_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
@@ -893,9 +915,9 @@ int cuadmm_solver_set_XyS(cuadmm_solver_t* s, const double* h_X, const double* h
         if (h_y) s->y.upload(h_y, s->con_num, s->stream);
         if (h_S) s->S.upload(h_S, s->nloc, s->stream);
         s->asmc_valid = false;
-        CUADMM_CUDA(cudaStreamSynchronize(s->stream));
-        CUADMM_CUDA(cudaMemcpyAsync(&s->st.p->sig, &sig, sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        CUADMM_CUDA(cudaStreamSynchronize(s->stream));
+        s->h_st->sig = sig;                 // pinned mirror: stays valid until the copy below has run
+        CUADMM_CUDA(cudaMemcpyAsync(&s->st.p->sig, &s->h_st->sig, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUADMM_CUDA(cudaStreamSynchronize(s->stream));      // the caller's host buffers may be reused on return
     });
 }
 
@@ -906,7 +928,7 @@ int cuadmm_solver_history(const cuadmm_solver_t* s, int which, double* out, int6
         CUADMM_REQUIRE(s && out, "null argument");
         CUADMM_REQUIRE(which >= 0 && which < 8, "which out of range");
         const int64_t n = std::min<int64_t>(cap, s->info_iter_num);
-        for (int64_t k = 0; k < n; ++k) out[k] = s->h_hist[(size_t)which * s->info_iter_num + k];
+        for (int64_t k = 0; k < n; ++k) out[k] = s->h_hist[which][(size_t)k];
     });
 }
 
@@ -970,7 +992,7 @@ int cuadmm_solve_matlab_like(int eig_stream_num_per_gpu, int max_iter, double st
             const int64_t cap = (int64_t)max_iter + 1;
             for (int q = 0; q < 8; ++q)
                 for (int64_t k = 0; k < cap; ++k)
-                    info[q * cap + k] = k < s.info_iter_num ? s.h_hist[(size_t)q * s.info_iter_num + k] : 0.0;
+                    info[q * cap + k] = k < s.info_iter_num ? s.h_hist[q][(size_t)k] : 0.0;
         }
         if (total_time) *total_time = s.total_time;
     });

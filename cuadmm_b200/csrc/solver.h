@@ -66,7 +66,7 @@ struct cuadmm_solver {
     cuadmm::DevBuf<double> X, S, y, Rp, SmC, Rd1, Rd, Xb, Xproj, rhsy, Cd, bd, normA;
     cuadmm::DevBuf<double> X_best, y_best, S_best;
     cuadmm::DevBuf<double> partial;          // per-CTA partial sums of the fused reductions
-    cuadmm::DevBuf<double> hist;             // 8 x hist_cap history (info_*_arr)
+    cuadmm::DevBuf<double> hist;             // 8 x hist_cap history ring (info_*_arr)
     int64_t hist_cap = 0;
     cuadmm::DevBuf<cuadmm::DevState> st;
     cuadmm::DevState* h_st = nullptr;        // pinned mirror
@@ -76,7 +76,7 @@ struct cuadmm_solver {
     double bscale = 1, Cscale = 1, objscale = 1, norm_borg = 1, norm_Corg = 1;
     std::vector<double> h_normA;
     int64_t info_iter_num = 0;
-    std::vector<double> h_hist;              // downloaded after solve
+    std::vector<double> h_hist[8];           // drained from the device ring while solve() runs
     double total_time = 0, init_time = 0, solve_time = 0, proj_time = 0, ysolve_time = 0, spmv_time = 0;
     int64_t launches = 0;
     int nA_blocks = 0, nAt_blocks = 0, nE_blocks = 0;

@@ -373,6 +373,58 @@ __global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t
 // are read (tile_ptr / tile_col: per tile row, runs of consecutive non-empty tiles as column
 // ranges): the inverse of the trailing factor block inherits
 // the block structure of the separators it came from and is often half empty.
+// dense tail, single GPU: out[i] = sum_j T[i, j] * in[j] for a row-major r x r triangular matrix (L22^-1 or its
+// transpose).  One warp per row, coalesced; only the 64-column tiles listed for the row's tile row
+// are read (tile_ptr / tile_col: per tile row, runs of consecutive non-empty tiles as column
+// ranges): the inverse of the trailing factor block inherits
+// the block structure of the separators it came from and is often half empty.
+__global__ void __launch_bounds__(256) tail_gemv_row_kernel(int64_t r, const double* __restrict__ T, const double* __restrict__ in,
+                                                        double* out, const int32_t* __restrict__ tile_ptr,
+                                                        const int32_t* __restrict__ tile_col, double* out_scatter,
+                                                        const int32_t* __restrict__ out_perm, int64_t perm_base,
+                                                        const int* __restrict__ done_flag, int longest_last) {
+    if (done_flag && *done_flag) return;
+    const int lane = threadIdx.x & 31;
+    // the CTAs with the longest rows go first (lower-triangular storage: the last rows), so the grid's tail
+    // wave is made of short rows
+    const int64_t cta = longest_last ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int64_t row = cta * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= r) return;
+    const double* Ti = T + row * r;
+    const int I = (int)(row >> 6);
+    double acc0 = 0.0, acc1 = 0.0;
+    const bool vec = (r & 1) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0;   // rows 16-byte aligned (tile columns are multiples of 64)
+    const bool in_al = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    for (int t = tile_ptr[I]; t < tile_ptr[I + 1]; ++t) {      // runs of consecutive non-empty tiles: [first, last) columns
+        const int64_t j0 = tile_col[2 * t];
+        const int64_t j1 = min((int64_t)tile_col[2 * t + 1], r);
+        if (vec) {
+            const int64_t jv = j0 + ((j1 - j0) & ~(int64_t)1);
+#pragma unroll 4
+            for (int64_t j = j0 + 2 * lane; j < jv; j += 64) {
+                const double2 a = __ldcs(reinterpret_cast<const double2*>(Ti + j));   // streamed once: evict first
+                const double2 b = in_al ? *reinterpret_cast<const double2*>(in + j) : make_double2(in[j], in[j + 1]);
+                acc0 = fma(a.x, b.x, acc0);
+                acc1 = fma(a.y, b.y, acc1);
+            }
+            if (lane == 0 && jv < j1) acc0 = fma(Ti[jv], in[jv], acc0);
+        } else {
+#pragma unroll 4
+            for (int64_t j = j0 + lane; j < j1; j += 32) acc0 = fma(Ti[j], in[j], acc0);
+        }
+    }
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        out[row] = acc;
+        if (out_scatter) out_scatter[out_perm[perm_base + row]] = acc;
+    }
+}
+
+// Sharded solver (and any launch over a SUBSET of the rows): the row-per-warp kernel above is bound by the dependent load
+// chain of its longest row (~30 us for 10k columns) however few rows it is given, so splitting rows over ranks buys
+// nothing with it.  Here:
 // One CTA = 8 consecutive rows x all their columns: warp w takes the 64-column chunks c == w (mod 8) of the tile row's
 // runs for ALL 8 rows (8 independent accumulators, the input chunk loaded once for the 8 rows), then the 8 x 8 partials
 // are reduced through shared memory.  A single row of 10k columns used to be one warp's dependent chain of ~160 loads
@@ -1226,10 +1278,11 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
                 tail_tcol_t.p, d_y_, perm.p, n_lead, done_flag, 0, tail_row0[1], n1, 0, PeerView(), PeerPtrs(), PeerPtrs());
         } else if (!peer || peer->world == 1) {
             const int blocks = (int)((n_tail + 7) / 8);
-            tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p, tail_tcol.p,
-                                                     nullptr, nullptr, 0, done_flag, 1, 0, n_tail, 0, PeerView(), PeerPtrs(), PeerPtrs());
-            tail_gemv_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p, tail_tcol_t.p,
-                                                     d_y_, perm.p, n_lead, done_flag, 0, 0, n_tail, 0, PeerView(), PeerPtrs(), PeerPtrs());
+            // whole matrix on one GPU: row per warp streams at 69 % of the HBM peak (ncu), the split-column kernel at 55 %
+            tail_gemv_row_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p, tail_tcol.p,
+                                                         nullptr, nullptr, 0, done_flag, 1);
+            tail_gemv_row_kernel<<<blocks, 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p, tail_tcol_t.p,
+                                                         d_y_, perm.p, n_lead, done_flag, 0);
         } else {
             PeerPtrs pxt = peer_x;
             for (int q = 0; q < peer->world; ++q) pxt.p[q] += n_lead;

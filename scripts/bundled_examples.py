@@ -7,9 +7,11 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from util_problems import load_fixture, make_solver
 SWITCH = int(os.environ.get("CUADMM_EX_SWITCH", "5000"))      # src/main.cu:39 passes 5000; solver.h:242 defaults to 11000
 CAP = int(os.environ.get("CUADMM_EX_CAP", "15000"))
-REF = {"pusht_n10": ("sGS-cuADMM.log", 30.3), "ros_2000": ("sGS-cuADMM.log", 1.3), "rose13": ("rose13.log", 3.5)}
+REF = {"pusht_n10": ("sGS-cuADMM.log", 30.3), "ros_2000": ("sGS-cuADMM.log", 1.3), "rose13": ("rose13.log", 3.5),
+       "planarhand_n1": ("PlanarHand_N=1_MOMENT/sGS-cuADMM.log (0.0961 s/iter incl. init; cuADMM.log: 0.0616)", 96.1),
+       "pendulum_n80": ("examples/pendulum/N=80_licols.log", 22.2), "pushbox_n50": (None, None)}
 out = []
-for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "c2b"]:
+for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "planarhand_n1", "pendulum_n80", "pushbox_n50", "c2b"]:
     if name == "c2b":       # the bench workload (synthetic, optimum known by construction)
         from cuadmm_b200.synthetic import c2b_blocks, chain_sdp
         P = chain_sdp(c2b_blocks(), 700000, seed=0)
@@ -25,7 +27,7 @@ for name in sys.argv[1:] or ["ros_2000", "pusht_n10", "rose13", "c2b"]:
     # time to the reference's own stop tolerance (src/main.cu:39: 1e-3) and to 1e-6, fresh solver
     for tol, key in ((1e-3, "to_1e-3"), (1e-6, "to_1e-6")):
         # rose13 needs 60,000 iterations in the reference's log: ms/iteration only; bounded GPU time otherwise
-        if name == "rose13" or (name == "c2b") != (tol == 1e-6):
+        if name in ("rose13", "pendulum_n80", "pushbox_n50") or (name == "c2b") != (tol == 1e-6):
             continue
         s2 = make_solver(P, verbose=False)
         cap = CAP
