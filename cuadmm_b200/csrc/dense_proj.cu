@@ -26,7 +26,13 @@
 
 namespace cuadmm {
 
-static constexpr int SG_M = 128, SG_N = 128, SG_K = 16, SG_PAD = 4, SG_THREADS = 256, SG_STAGES = 4;
+#ifndef CUADMM_SG_K
+#define CUADMM_SG_K 16
+#endif
+#ifndef CUADMM_SG_STAGES
+#define CUADMM_SG_STAGES 4
+#endif
+static constexpr int SG_M = 128, SG_N = 128, SG_K = CUADMM_SG_K, SG_PAD = 4, SG_THREADS = 256, SG_STAGES = CUADMM_SG_STAGES;
 static constexpr size_t SG_SMEM = sizeof(double) * SG_STAGES * SG_K * ((SG_M + SG_PAD) + (SG_N + SG_PAD));
 
 struct DenseDesc {
@@ -152,8 +158,8 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
             // A tile 128 (m) x 16 (k): element (mm, kk) at A[m0+mm + (k0+kk) ld] (contiguous along m); same for B
             // through its transpose: B(kk, nn) = B(nn, kk) at B[n0+nn + (k0+kk) ld]
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int e = tid + t * SG_THREADS;            // 1024 16-byte chunks per operand
+            for (int t = 0; t < SG_K / 4; ++t) {
+                const int e = tid + t * SG_THREADS;            // 64 16-byte chunks per k-row and operand
                 const int mm = (e & 63) * 2, kk = e >> 6;
                 const int gk = k0 + kk;
                 const int gm = m0 + mm, gn = n0 + mm;
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
             }
         } else {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < SG_K / 2; ++t) {
                 const int e = tid + t * SG_THREADS;
                 const int mm = e & 127, kk = e >> 7;
                 const int gk = k0 + kk;

@@ -42,6 +42,8 @@ struct cuadmm_plan {
     void reset_warm_start();
     double threshold = 1e-11;     // columns of G count as orthogonal when every |cos| <= threshold (tested on the state after each sweep)
     int max_sweeps = 40;
+    bool force_global = false;    // every block above the shared-memory classes on the global-memory Jacobi kernel (eigenvalue debug plan)
+    std::unique_ptr<cuadmm_plan> eig_plan;   // lazily built shadow plan: eigenvalues of the blocks on the dense sign path (debug entry only)
     bool use_gram = true;         // CUADMM_JACOBI_GRAM=0: round-1 stopping rule (a whole sweep without a cosine above the threshold)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> side_streams;    // classes run concurrently on these

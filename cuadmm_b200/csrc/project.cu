@@ -62,23 +62,11 @@ __device__ __forceinline__ double mat_max(double v, double* red, int tid) {
 // Column stride ld == L (mod 16) makes the L-row windows of the 16/L consecutive round-robin
 // columns a half-warp touches fall into disjoint banks.
 // ------------------------------------------------------------------------------------------
-// 16-byte sweep accesses (two rows per lane) were measured 10 % SLOWER than the 8-byte ones on B200 (the ld == 8 mod 16
-// layout they need costs the other phases their conflict-free column windows): off by default, kept for experiments
-#ifndef CUADMM_JACOBI_VEC
-#define CUADMM_JACOBI_VEC 0
-#endif
+// (16-byte sweep accesses — two rows per lane, ld == 8 mod 16 — were measured 10 % slower on B200: profiles/ncu_r02.md)
 __host__ __device__ __forceinline__ int jacobi_ld(int n, int L) {
     if (L >= 16) return n | 1;
-    // L == 4: the sweep moves two rows per lane with 16-byte shared-memory accesses; a quarter-warp (two pairs' groups,
-    // 64 contiguous bytes each) is conflict-free when consecutive round-robin columns are 64 bytes apart mod 128:
-    // ld == 8 (mod 16).  L == 8: 8-byte accesses, ld == 8 (mod 16) as before.
-#if CUADMM_JACOBI_VEC
-    const int want = 8;
-#else
-    const int want = L & 15;
-#endif
     int ld = n;
-    while ((ld & 15) != want) ++ld;
+    while ((ld & 15) != (L & 15)) ++ld;
     return ld;
 }
 __host__ __device__ __forceinline__ size_t jacobi_per_mat(int nmax, int L) {
@@ -340,8 +328,6 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
     const double tiny2 = 1.2325951644078309e-32;  // 2^-106: rotations below rounding level are skipped
     int sweeps = 0;
     bool converged = false;
-    // L == 4: two adjacent rows per lane and access (16-byte shared-memory loads / stores): row pair (2*lane + 2*L*i)
-    constexpr bool VEC = CUADMM_JACOBI_VEC && (L == 4) && (RPL % 2 == 0);
     while (true) {
         // refresh the tracked squared norms from the data
         for (int j = grp; j < n; j += NG) {
@@ -366,32 +352,15 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
                 double* __restrict__ Gq = G + q * ld;
                 double gp[RPL], gq[RPL];
                 double ga = 0.0, gb = 0.0;
-                if (VEC) {
 #pragma unroll
-                    for (int i = 0; i < RPL / 2; ++i) {
-                        const int r = 2 * (lane + i * L);
-                        if (r < n) {             // ld is even and G is zero-free beyond n only up to ld: row r + 1 < ld always
-                            const double2 vp = *reinterpret_cast<const double2*>(Gp + r);
-                            const double2 vq = *reinterpret_cast<const double2*>(Gq + r);
-                            gp[2 * i] = vp.x; gq[2 * i] = vq.x;
-                            gp[2 * i + 1] = (r + 1 < n) ? vp.y : 0.0; gq[2 * i + 1] = (r + 1 < n) ? vq.y : 0.0;
-                            ga = fma(gp[2 * i], gq[2 * i], ga);
-                            gb = fma(gp[2 * i + 1], gq[2 * i + 1], gb);
-                        } else {
-                            gp[2 * i] = 0.0; gq[2 * i] = 0.0; gp[2 * i + 1] = 0.0; gq[2 * i + 1] = 0.0;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < RPL; ++i) {
-                        const int r = lane + i * L;
-                        if (r < n) {
-                            gp[i] = Gp[r];
-                            gq[i] = Gq[r];
-                            if (i & 1) gb = fma(gp[i], gq[i], gb); else ga = fma(gp[i], gq[i], ga);
-                        } else {
-                            gp[i] = 0.0; gq[i] = 0.0;
-                        }
+                for (int i = 0; i < RPL; ++i) {
+                    const int r = lane + i * L;
+                    if (r < n) {
+                        gp[i] = Gp[r];
+                        gq[i] = Gq[r];
+                        if (i & 1) gb = fma(gp[i], gq[i], gb); else ga = fma(gp[i], gq[i], ga);
+                    } else {
+                        gp[i] = 0.0; gq[i] = 0.0;
                     }
                 }
                 ga += gb;
@@ -403,28 +372,12 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
                 if (g2 > tiny2 * ab) {
                     double c, sn, an, bn;
                     jacobi_cs2(al, be, ga, c, sn, an, bn);
-                    if (VEC) {
 #pragma unroll
-                        for (int i = 0; i < RPL / 2; ++i) {
-                            const int r = 2 * (lane + i * L);
-                            if (r < n) {
-                                double2 op, oq;
-                                op.x = fma(c, gp[2 * i], -sn * gq[2 * i]);
-                                oq.x = fma(sn, gp[2 * i], c * gq[2 * i]);
-                                op.y = fma(c, gp[2 * i + 1], -sn * gq[2 * i + 1]);
-                                oq.y = fma(sn, gp[2 * i + 1], c * gq[2 * i + 1]);
-                                *reinterpret_cast<double2*>(Gp + r) = op;
-                                *reinterpret_cast<double2*>(Gq + r) = oq;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < RPL; ++i) {
-                            const int r = lane + i * L;
-                            if (r < n) {
-                                Gp[r] = fma(c, gp[i], -sn * gq[i]);
-                                Gq[r] = fma(sn, gp[i], c * gq[i]);
-                            }
+                    for (int i = 0; i < RPL; ++i) {
+                        const int r = lane + i * L;
+                        if (r < n) {
+                            Gp[r] = fma(c, gp[i], -sn * gq[i]);
+                            Gq[r] = fma(sn, gp[i], c * gq[i]);
                         }
                     }
                     if (lane == 0) { w[p] = an; w[q] = bn; }
@@ -807,7 +760,7 @@ void cuadmm_plan::build_device() {
     const std::vector<SizeClass> table = size_classes();
     std::vector<std::vector<int64_t>> members(table.size() + 1);
     const char* large_env = getenv("CUADMM_LARGE");           // "jacobi": global-memory Jacobi for n > 168 (debug)
-    const bool large_dense = !(large_env && !strcmp(large_env, "jacobi"));
+    const bool large_dense = !(force_global || (large_env && !strcmp(large_env, "jacobi")));
     std::vector<int64_t> dense_blocks;
     for (int64_t k = 0; k < nblk; ++k) {
         const int n = layout.blk[k];
@@ -1090,6 +1043,37 @@ static void project_host_impl(cuadmm_plan* plan, const double* h_Xb, double* h_X
     float ms = 0.f;
     CUADMM_CUDA(cudaEventElapsedTime(&ms, plan->ev0, plan->ev1));
     plan->last_ms = ms;
+    if (h_eig && plan->dense) {
+        // The sign iteration of the large blocks (n > 168) yields the projection but no eigenvalues.  For this parity / debug
+        // entry they come from the global-memory Jacobi kernel run on a shadow plan over those blocks (n <= 1024: beyond
+        // that it is too slow to be useful and the slots stay NaN).  The solver never needs eigenvalues.
+        const std::vector<int32_t>& blk = plan->layout.blk;
+        std::vector<int64_t> which;
+        for (size_t k = 0; k < blk.size(); ++k) if (blk[k] > 168 && blk[k] <= 1024) which.push_back((int64_t)k);
+        if (!which.empty()) {
+            std::vector<int32_t> sb;
+            for (int64_t k : which) sb.push_back(blk[k]);
+            if (!plan->eig_plan || plan->eig_plan->layout.blk != sb) {
+                plan->eig_plan.reset(new cuadmm_plan());
+                plan->eig_plan->layout.init(sb.data(), (int64_t)sb.size());
+                plan->eig_plan->device = plan->device;
+                plan->eig_plan->force_global = true;
+                plan->eig_plan->build_device();
+            }
+            cuadmm_plan* E = plan->eig_plan.get();
+            std::vector<double> xin((size_t)E->layout.vec_len), xout((size_t)E->layout.vec_len), ev((size_t)(E->layout.sum_large_mat_size + E->layout.sum_small_mat_size));
+            for (size_t i = 0; i < which.size(); ++i)
+                std::copy(h_Xb + plan->layout.svec_off[which[i]], h_Xb + plan->layout.svec_off[which[i] + 1], xin.begin() + E->layout.svec_off[i]);
+            project_host_impl(E, xin.data(), xout.data(), ev.data(), nullptr);
+            std::vector<int64_t> w_off(blk.size() + 1, 0);
+            for (size_t k = 0; k < blk.size(); ++k) w_off[k + 1] = w_off[k] + blk[k];
+            int64_t eo = 0;
+            for (size_t i = 0; i < which.size(); ++i) {
+                std::copy(ev.begin() + eo, ev.begin() + eo + sb[i], h_eig + w_off[which[i]]);
+                eo += sb[i];
+            }
+        }
+    }
     if (h_eig) {
         // ascending per block, like dsyevd / Xsyevd / syevj(sort=1)
         int64_t o = 0;

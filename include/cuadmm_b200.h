@@ -87,7 +87,10 @@ int cuadmm_project_psd(cuadmm_plan* plan, const double* d_Xb, double* d_Xproj, v
 /* same, host buffers (H2D + kernel + D2H inside the call) */
 int cuadmm_project_psd_host(cuadmm_plan* plan, const double* h_Xb, double* h_Xproj);
 /* parity/debug: also returns per-block eigenvalues ascending, concatenated in blk
- * order (length sum n_k), and the Jacobi sweep count per block (may be NULL) */
+ * order (length sum n_k), and the Jacobi sweep count per block (may be NULL).
+ * Blocks n <= 168: eigenvalues of the kernel that produced X.  168 < n <= 1024: X comes from the sign
+ * iteration, which has no eigenvalues; they are computed by the global-memory Jacobi kernel on the same
+ * input for this entry only.  n > 1024: NaN. */
 int cuadmm_project_psd_eig_host(cuadmm_plan* plan, const double* h_Xb, double* h_Xproj,
                                 double* h_eigvals, int32_t* h_sweeps);
 /* device time of the last cuadmm_project_psd* call in ms (CUDA events) */
