@@ -22,7 +22,10 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(128) dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha,
                                                     const double* __restrict__ A, int64_t lda,
                                                     const double* __restrict__ B, int64_t ldb,
-                                                    double beta, double* C, int64_t ldc) {
+                                                    double beta, double* C, int64_t ldc, int shape) {
+    // shape 1: only the tiles on or below the diagonal are computed (symmetric rank-k updates whose consumer reads the
+    // lower triangle); shape 2: op(B) is lower triangular, so output column tile n0 only needs k >= n0
+    if (shape == 1 && (int64_t)blockIdx.y * GB_N > (int64_t)blockIdx.x * GB_M + (GB_M - 1)) return;
     __shared__ double As[2][GB_K][GB_M + GB_PAD];
     __shared__ double Bs[2][GB_K][GB_N + GB_PAD];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -60,9 +63,10 @@ __global__ void __launch_bounds__(128) dgemm_kernel(int64_t m, int64_t n, int64_
     };
 
     const int64_t nk = (k + GB_K - 1) / GB_K;
-    if (nk > 0) load_tiles(0, 0);
+    const int64_t kt0 = (shape == 2) ? ((n0 / GB_K < nk) ? n0 / GB_K : nk) : 0;
+    if (nk > kt0) load_tiles((int)(kt0 & 1), kt0 * GB_K);
     __syncthreads();
-    for (int64_t kt = 0; kt < nk; ++kt) {
+    for (int64_t kt = kt0; kt < nk; ++kt) {
         const int buf = (int)(kt & 1);
         if (kt + 1 < nk) load_tiles(buf ^ 1, (kt + 1) * GB_K);
 #pragma unroll
@@ -95,13 +99,13 @@ __global__ void __launch_bounds__(128) dgemm_kernel(int64_t m, int64_t n, int64_
 }
 
 void dgemm(cudaStream_t st, bool transA, bool transB, int64_t m, int64_t n, int64_t k, double alpha,
-           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int shape) {
     if (m <= 0 || n <= 0) return;
     dim3 grid((unsigned)((m + GB_M - 1) / GB_M), (unsigned)((n + GB_N - 1) / GB_N));
-    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else dgemm_kernel<true, true><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, shape);
+    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, shape);
+    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, shape);
+    else dgemm_kernel<true, true><<<grid, 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, shape);
     CUADMM_CUDA(cudaGetLastError());
 }
 
@@ -176,7 +180,7 @@ void potrf_lower(cudaStream_t st, int64_t n, double* A, int64_t lda, double* inv
                                           sizeof(double) * below, nb, cudaMemcpyDeviceToDevice, st));
             // trailing <- trailing - panel * panel^T
             double* A22 = A + (j + nb) + (j + nb) * lda;
-            dgemm(st, false, true, below, below, nb, -1.0, Aij, lda, Aij, lda, 1.0, A22, lda);
+            dgemm(st, false, true, below, below, nb, -1.0, Aij, lda, Aij, lda, 1.0, A22, lda, 1);   // lower tiles only
         }
     }
     CUADMM_CUDA(cudaGetLastError());
@@ -199,7 +203,7 @@ void trtri_lower(cudaStream_t st, int64_t n, const double* L, int64_t ldl, const
         copy_inv_block_kernel<<<1, 256, 0, st>>>(nb, invi, X + i + i * ldx, ldx);
         if (i > 0) {
             // T = L(i, 0:i) * X(0:i, 0:i) ; X(i, 0:i) = -inv_ii * T
-            dgemm(st, false, false, nb, i, i, 1.0, L + i, ldl, X, ldx, 0.0, T.p, NB);
+            dgemm(st, false, false, nb, i, i, 1.0, L + i, ldl, X, ldx, 0.0, T.p, NB, 2);            // X(0:i, 0:i) is lower triangular
             dgemm(st, false, false, nb, i, nb, -1.0, invi, NB, T.p, NB, 0.0, X + i, ldx);
         }
     }
@@ -283,7 +287,7 @@ void build_dense_tail(const SymCsc& C, const CholFactor& F, int64_t n_lead, int6
             DevBuf<int32_t> dr, dc; DevBuf<double> dv;
             dr.upload(rr, st); dc.upload(cc, st); dv.upload(vv, st);
             scatter_coo_kernel<<<(unsigned)((vv.size() + 255) / 256), 256, 0, st>>>((int64_t)vv.size(), dr.p, dc.p, dv.p, B.p, r, 0);
-            dgemm(st, false, true, r, r, w, -1.0, B.p, r, B.p, r, 1.0, S.p, r);
+            dgemm(st, false, true, r, r, w, -1.0, B.p, r, B.p, r, 1.0, S.p, r, 1);                  // the factorisation reads the lower triangle
             CUADMM_CUDA(cudaStreamSynchronize(st));
         }
     }

@@ -7,8 +7,10 @@
 namespace cuadmm {
 
 // C(m x n) = alpha * op(A) * op(B) + beta * C      (column-major, FP64 tensor-core mma.sync)
+// shape 0: general; 1: only the 64 x 64 tiles on or below the diagonal of C are computed (symmetric updates read through
+// the lower triangle); 2: op(B) is lower triangular (k x n with zeros above the diagonal): column tile n0 starts at k = n0
 void dgemm(cudaStream_t st, bool transA, bool transB, int64_t m, int64_t n, int64_t k, double alpha,
-           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int shape = 0);
 
 // in-place blocked Cholesky of the lower triangle; *d_info counts pivots <= pivot_floor[k] (treated
 // as redundant directions: L_kk = +inf).

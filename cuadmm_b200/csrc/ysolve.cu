@@ -8,6 +8,9 @@
 // chain), a sparse backward sweep with the scatter-permute fused in.  Nothing leaves the GPU and
 // there is no host synchronisation.
 #include "ysolve.h"
+#include <chrono>
+#include <thread>
+#include <atomic>
 #include "dense.h"
 #include <algorithm>
 #include <numeric>
@@ -669,10 +672,14 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     int64_t n_collapsed = 0, levels_before = 0, levels_after = 0, chain_entries = 0;
     kind.assign(H.n_sub, 0);
     auto same = [&](int32_t u, int64_t p) { return H.sub[H.dep[p]] == H.sub[u]; };
-    for (int64_t t = 0; t < H.n_sub && use_packed; ++t) {
+    // one subtree at a time, on a pool of host threads: subtrees own disjoint rows of the scratch arrays (loc, cidx, height,
+    // lvl_r), results land in per-subtree slots and are collected in subtree order afterwards (deterministic layout)
+    std::vector<Packed> result(use_packed ? H.n_sub : 0);
+    std::atomic<int64_t> a_collapsed{0}, a_before{0}, a_after{0}, a_entries{0};
+    auto do_subtree = [&](int64_t t) {
         const std::vector<int32_t>& rows = members[t];       // in solve order
         const int32_t nr0 = (int32_t)rows.size();
-        if (nr0 + chain_max > kPkMaxRows) continue;
+        if (nr0 + chain_max > kPkMaxRows) return;
         int32_t longest = 0;
         for (int32_t q = 0; q < nr0; ++q) {
             const int32_t u = rows[q];
@@ -681,7 +688,7 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
             for (int64_t p = H.ptr[u]; p < H.ptr[u + 1]; ++p) cnt += same(u, p) ? 1 : 0;
             longest = std::max(longest, cnt);
         }
-        if (longest > kPkMaxRowEntries) continue;
+        if (longest > kPkMaxRowEntries) return;
         // ---- chain collapse: pick C
         std::vector<int32_t> C;
         int new_depth = depth[t], k0 = 0;
@@ -745,7 +752,7 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
                 PkRow r; r.slot = loc[C[i]]; r.invd = -1.0;
                 const double* mi = M.data() + (size_t)i * nC;
                 for (int32_t j = 0; j <= i; ++j) if (mi[j] != 0.0) { r.idx.push_back((uint16_t)(nr0 + j)); r.val.push_back(mi[j]); }
-                chain_entries += (int64_t)r.idx.size();
+                a_entries += (int64_t)r.idx.size();
                 lv[lvB].push_back(std::move(r));
             }
             if (initial) {
@@ -766,10 +773,10 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
                     if (!r.idx.empty()) lv[k0].push_back(std::move(r));
                 }
             }
-            ++n_collapsed; levels_before += depth[t]; levels_after += new_depth;
+            ++a_collapsed; a_before += depth[t]; a_after += new_depth;
         }
         // ---- records and chunks
-        Packed P; P.t = (int32_t)t; P.last_used = 0; P.levels = new_depth;
+        Packed& P = result[t]; P.t = (int32_t)t; P.last_used = 0; P.levels = new_depth;
         P.slot_u.assign(nr0 + nC, -1); P.slot_src.assign(nr0 + nC, -1);
         for (int32_t q = 0; q < nr0; ++q) {
             const int32_t u = rows[q];
@@ -783,7 +790,10 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
             if (rec_rel.empty()) return;
             seg_end.push_back((uint16_t)rec_rel.size());
             const size_t db = dir_bytes(seg_end.size(), rec_rel.size());
-            std::vector<unsigned char> chunk(kPkChunk, 0);
+            // a chunk is stored unpadded until another one follows it (tens of thousands of tiny subtrees have one short
+            // chunk each: padding every one to kPkChunk zero-filled gigabytes at init)
+            if (!P.bytes.empty()) P.bytes.resize((P.bytes.size() + kPkChunk - 1) / kPkChunk * kPkChunk, 0);
+            std::vector<unsigned char> chunk((db + recs.size() + 15) / 16 * 16, 0);
             uint16_t* dir = reinterpret_cast<uint16_t*>(chunk.data());
             dir[0] = (uint16_t)seg_end.size(); dir[1] = (uint16_t)rec_rel.size();
             for (size_t i = 0; i < seg_end.size(); ++i) dir[2 + i] = seg_end[i];
@@ -845,15 +855,35 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
         }
         close_chunk();
         for (int32_t u : C) cidx[u] = -1;
-        if (nC == 0 && nr0 <= kPkWarpRows && P.bytes.size() == (size_t)kPkChunk && P.last_used <= (size_t)kPkWarpBlob) {
+        if (nC == 0 && nr0 <= kPkWarpRows && P.bytes.size() <= (size_t)kPkChunk && P.last_used <= (size_t)kPkWarpBlob) {
             P.bytes.resize((P.last_used + 15) / 16 * 16);
             kind[t] = 1;
-            blobs.push_back(std::move(P));
         } else {
             kind[t] = 2;
-            packs.push_back(std::move(P));
+        }
+    };
+    if (use_packed && H.n_sub > 0) {
+        int nthreads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+        if (const char* e = getenv("CUADMM_INIT_THREADS")) nthreads = std::max(1, atoi(e));
+        nthreads = (int)std::min<int64_t>(nthreads, H.n_sub);
+        std::atomic<int64_t> next{0};
+        std::vector<std::string> errors(nthreads);
+        auto worker = [&](int id) {
+            try {
+                for (int64_t t = next.fetch_add(1); t < H.n_sub; t = next.fetch_add(1)) do_subtree(t);
+            } catch (const std::exception& ex) { errors[id] = ex.what(); next.store(H.n_sub); }
+        };
+        std::vector<std::thread> pool;
+        for (int i = 1; i < nthreads; ++i) pool.emplace_back(worker, i);
+        worker(0);
+        for (auto& th : pool) th.join();
+        for (const std::string& e : errors) if (!e.empty()) throw Error(CUADMM_EINVAL, e);
+        for (int64_t t = 0; t < H.n_sub; ++t) {
+            if (kind[t] == 1) blobs.push_back(std::move(result[t]));
+            else if (kind[t] == 2) packs.push_back(std::move(result[t]));
         }
     }
+    n_collapsed = a_collapsed; levels_before = a_before; levels_after = a_after; chain_entries = a_entries;
     S.n_sub_pack = (int64_t)packs.size();
     S.n_sub_warp = (int64_t)blobs.size();
     S.pk_smem = 0; S.pk_rows = 0;
@@ -882,6 +912,7 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     };
     for (const Packed& P : packs) {
         stream.insert(stream.end(), P.bytes.begin(), P.bytes.end());
+        stream.resize((stream.size() + kPkChunk - 1) / kPkChunk * kPkChunk, 0);      // the last chunk of a pack is stored unpadded
         chunk_off.push_back((int64_t)(stream.size() / kPkChunk));
         add_slots(P);
     }
@@ -908,7 +939,7 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
     if (getenv("CUADMM_YSOLVE_TIMELINE") && !packs.empty()) {   // debug: per-CTA globaltimer stamps of tri_packed_kernel
         S.pk_timeline.alloc(4 * (int64_t)packs.size());
         std::vector<long long> meta;
-        for (const Packed& P : packs) { meta.push_back((long long)(P.bytes.size() / kPkChunk)); meta.push_back((long long)P.slot_u.size()); meta.push_back(P.levels); }
+        for (const Packed& P : packs) { meta.push_back((long long)((P.bytes.size() + kPkChunk - 1) / kPkChunk)); meta.push_back((long long)P.slot_u.size()); meta.push_back(P.levels); }
         S.pk_timeline_meta = meta;
     }
     S.pk_smem = (size_t)kPkRing * kPkChunk + 64 + sizeof(double) * (size_t)cta_slots;
@@ -917,7 +948,7 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
         fprintf(stderr, "[ysolve] %s packed: %zu CTA subtrees in %lld chunks (largest %zu), %zu warp subtrees in %zu bytes, "
                 "%lld slots, %lld external entries (%lld heavy rows), smem %zu; chains collapsed in %lld subtrees (%lld -> %lld levels, %lld inverse entries)\n",
                 H.subtrees_first ? "fwd" : "bwd", packs.size(), (long long)chunk_off.back(),
-                packs.empty() ? (size_t)0 : packs[0].bytes.size() / kPkChunk, blobs.size(), blob_bytes.size(), (long long)S.pk_rows,
+                packs.empty() ? (size_t)0 : (packs[0].bytes.size() + kPkChunk - 1) / kPkChunk, blobs.size(), blob_bytes.size(), (long long)S.pk_rows,
                 (long long)ext_ptr.back(), (long long)S.pk_n_heavy, S.pk_smem, (long long)n_collapsed, (long long)levels_before, (long long)levels_after,
                 (long long)chain_entries);
 }
@@ -1090,12 +1121,23 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
     Y->device = device; Y->m = m;
     DeviceGuard g(device);
 
-    // ---- host analysis
+    // ---- host analysis (CUADMM_YSOLVE_VERBOSE prints the wall time of every phase)
+    const bool vtime = getenv("CUADMM_YSOLVE_VERBOSE") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!vtime) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ysolve] init %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+        tp0 = t;
+    };
     SymCsc M = form_aat(m, vec_len, rowptr, colind, val, eps);
+    lap("A A^T");
     Y->nnz_aat = M.p[m];
     std::vector<int32_t> perm0 = min_degree_order(M);
+    lap("minimum-degree ordering");
     CholFactor F;
     chol_symbolic(M, perm0, F, nullptr);
+    lap("symbolic (1)");
     std::vector<int32_t> lev;
     const int64_t cut = choose_tail(F, lev);
     std::vector<int32_t> perm1; perm1.reserve(m);
@@ -1110,7 +1152,9 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
     } else {
         chol_symbolic(M, perm0, F, &C);
     }
+    lap("symbolic (2, tail last)");
     chol_numeric(C, F, n_lead);
+    lap("numeric (sparse lead part)");
     Y->n_lead = n_lead; Y->n_tail = n_tail;
     Y->nnz_L = F.nnz();
     Y->n_deficient = F.n_deficient;
@@ -1165,6 +1209,7 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         H.out_perm = &Y->h_perm;
         upload_sweep(H, Y->bwd);
     }
+    lap("pack + upload sweeps");
     Y->z.alloc(std::max<int64_t>(m, 1));
     Y->x.alloc(std::max<int64_t>(m, 1));
 
@@ -1197,6 +1242,7 @@ cuadmm_ysolve_s* ysolve_create(int64_t m, int64_t vec_len, int64_t nnz, const in
         Y->tail_tptr.upload(tp); Y->tail_tcol.upload(tc); Y->tail_tptr_t.upload(tpt); Y->tail_tcol_t.upload(tct);
         Y->n_deficient += tail_def;
         Y->tail_tmp.alloc(n_tail);
+        lap("dense tail (GPU)");
     }
     Y->launches_per_solve = (int)(Y->fwd.phases.size() + Y->bwd.phases.size()) + (n_tail > 0 ? 2 : 0) +
                             (Y->fwd.n_sub_cta > 0 ? 2 : 0) + (Y->fwd.n_sub_warp > 0 ? 2 : 0) + (Y->fwd.n_sub_pack > 0 ? 2 : 0) +
