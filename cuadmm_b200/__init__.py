@@ -18,7 +18,7 @@ if not _os.path.exists(LIB_PATH):
         "`python -c 'import __graft_entry__ as g; g.build()'`). There is no pure-Python fallback.")
 
 _API = ("lib", "CuadmmError", "Plan", "SpMV", "YSolve", "Solver", "Problem", "device_count", "version",
-        "normA_host", "csc_to_csr_host", "Shard", "nccl_unique_id", "unique_id", "solve_matlab_like")
+        "normA_host", "csc_to_csr_host", "Shard", "nccl_unique_id", "unique_id", "solve_matlab_like", "eig_rank_mask")
 
 
 def __getattr__(name):

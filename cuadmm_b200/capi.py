@@ -77,6 +77,8 @@ _sig("cuadmm_plan_maps", C.c_int, vp, c_i32p, c_i32p, c_i32p)
 _sig("cuadmm_plan_partition", C.c_int, vp, C.c_int, c_i32p, c_f64p)
 _sig("cuadmm_plan_set_jacobi", C.c_int, vp, C.c_double, C.c_int)
 _sig("cuadmm_plan_set_warm_start", C.c_int, vp, C.c_int)
+_sig("cuadmm_plan_set_rank_limit", C.c_int, vp, C.c_int)
+_sig("cuadmm_eig_rank_mask", C.c_int, c_i32p, C.c_int64, C.c_int64, C.c_int64)
 _sig("cuadmm_plan_last_ms", C.c_double, vp)
 _sig("cuadmm_plan_last_launches", C.c_int64, vp)
 _sig("cuadmm_project_psd", C.c_int, vp, vp, vp, vp)
@@ -147,6 +149,10 @@ class Plan:
 
     def set_warm_start(self, enable):
         _check(lib.cuadmm_plan_set_warm_start(self.h, 1 if enable else 0))
+
+    def set_rank_limit(self, eig_rank):
+        """fixed-rank projection: keep only the eig_rank largest eigenvalues of every block (0: off)"""
+        _check(lib.cuadmm_plan_set_rank_limit(self.h, int(eig_rank)))
 
     def project_host(self, Xb):
         Xb = _f64(Xb)
@@ -337,6 +343,13 @@ def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _check(lib.cuadmm_nccl_unique_id(buf))
     return buf.raw
+
+
+def eig_rank_mask(batch_size, mat_size, eig_rank):
+    """get_eig_rank_mask of the reference (src/utils/get_eig_rank_mask.cu)"""
+    mask = np.zeros(batch_size * mat_size, np.int32)
+    _check(lib.cuadmm_eig_rank_mask(_p(mask, c_i32p), batch_size, mat_size, eig_rank))
+    return mask
 
 
 def unique_id():

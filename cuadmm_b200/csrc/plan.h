@@ -44,6 +44,7 @@ struct cuadmm_plan {
     int max_sweeps = 40;
     bool force_global = false;    // every block above the shared-memory classes on the global-memory Jacobi kernel (eigenvalue debug plan)
     std::unique_ptr<cuadmm_plan> eig_plan;   // lazily built shadow plan: eigenvalues of the blocks on the dense sign path (debug entry only)
+    int rank_limit = 0;           // > 0: fixed-rank projection (cuadmm_plan_set_rank_limit)
     bool use_gram = true;         // CUADMM_JACOBI_GRAM=0: round-1 stopping rule (a whole sweep without a cosine above the threshold)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> side_streams;    // classes run concurrently on these

@@ -424,6 +424,21 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
     } else {
         mat_sync<WARP>();
     }
+    if (a.rank_limit > 0) {
+        // fixed-rank projection (max_dense_vector_zero_mask with the mask of get_eig_rank_mask, src/kernels/dense_scalar.cu:51-56,
+        // src/utils/get_eig_rank_mask.cu:16-38): only the rank_limit LARGEST eigenvalues of the block may survive the clamp.
+        // The rebuild weight is increasing in the eigenvalue on (0, ||A||], so ranking weights ranks eigenvalues.
+        int drop = 0;
+        if (tid < n && w[tid] > 0.0) {
+            const double mine = w[tid];
+            int rank = 0;
+            for (int k = 0; k < n; ++k) { const double o = w[k]; rank += (o > mine || (o == mine && k > tid)) ? 1 : 0; }
+            drop = rank >= a.rank_limit;
+        }
+        mat_sync<WARP>();
+        if (drop) w[tid] = 0.0;
+        mat_sync<WARP>();
+    }
     if (tid == 0) {
         int k = 0;
         for (int j = 0; j < n; ++j) if (w[j] > 0.0) pos[k++] = j;
@@ -878,6 +893,10 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
     // streams so that small, mid and large blocks overlap (class 0 stays on the caller's stream when
     // there is no dense part)
     const bool has_dense = dense != nullptr;
+    if (rank_limit > 0) {
+        if (has_dense) throw Error(CUADMM_EINVAL, "fixed-rank projection is only available for blocks n <= 168 (the sign iteration of larger blocks has no eigenvalues to rank)");
+        for (const Class& cl : classes) if (cl.kind == kGlobalKind) throw Error(CUADMM_EINVAL, "fixed-rank projection is only available for blocks n <= 168");
+    }
     if (classes.size() > 1 || (has_dense && !classes.empty())) CUADMM_CUDA(cudaEventRecord(fork_event, stream));
     for (size_t i = 0; i < classes.size(); ++i) {
         const Class& cl = classes[i];
@@ -898,6 +917,7 @@ int cuadmm_plan::project(const double* d_Xb, double* d_Xproj, cudaStream_t strea
         a.scratch = d_scratch.p;
         a.done_flag = done_flag;
         a.use_gram = use_gram ? 1 : 0;
+        a.rank_limit = rank_limit;
         a.Q = (warm_start && cl.kind != kGlobalKind && d_Q.n > 0) ? d_Q.p : nullptr;
         if (epi) a.epi = *epi; else { a.epi.X = nullptr; a.epi.Rd1 = nullptr; a.epi.Cd = nullptr; a.epi.S = nullptr; a.epi.SmC = nullptr; a.epi.sig_ptr = nullptr; }
         if (cl.kind == kGlobalKind) {
@@ -993,6 +1013,25 @@ int cuadmm_plan_partition(const cuadmm_plan* plan, int nparts, int32_t* owner, d
     return guarded([&] {
         CUADMM_REQUIRE(plan && owner, "null argument");
         plan->layout.partition(nparts, owner, part_cost);
+    });
+}
+
+int cuadmm_plan_set_rank_limit(cuadmm_plan* plan, int eig_rank) {
+    return guarded([&] {
+        CUADMM_REQUIRE(plan, "plan is null");
+        CUADMM_REQUIRE(eig_rank >= 0, "eig_rank < 0");
+        plan->rank_limit = eig_rank;
+    });
+}
+
+// get_eig_rank_mask (src/utils/get_eig_rank_mask.cu:16-38): 1 on the last eig_rank positions of every block of mat_size
+int cuadmm_eig_rank_mask(int32_t* mask, int64_t batch_size, int64_t mat_size, int64_t eig_rank) {
+    return guarded([&] {
+        CUADMM_REQUIRE(mask || batch_size * mat_size == 0, "mask is null");
+        CUADMM_REQUIRE(batch_size >= 0 && mat_size >= 0 && eig_rank >= 0 && eig_rank <= mat_size, "bad sizes");
+        for (int64_t i = 0; i < batch_size * mat_size; ++i) mask[i] = 0;
+        for (int64_t i = 0; i < batch_size; ++i)
+            for (int64_t j = 0; j < eig_rank; ++j) mask[i * mat_size + (mat_size - 1 - j)] = 1;
     });
 }
 

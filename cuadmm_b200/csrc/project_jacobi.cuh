@@ -66,6 +66,7 @@ struct ProjArgs {
     double* scratch;        // global variant
     const int* done_flag;   // optional device flag: kernels return at once when *done_flag != 0
     int use_gram;           // 1: convergence tested on the state after each sweep (Gram matrix on the tensor cores)
+    int rank_limit;         // > 0: fixed-rank projection, only the rank_limit largest eigenvalues survive the clamp
     double* Q;              // optional (null): warm-start bases, n x n column-major at desc.q_off, read AND updated
     ProjEpilogue epi;
 };

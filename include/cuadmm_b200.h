@@ -100,6 +100,12 @@ int64_t cuadmm_plan_last_launches(const cuadmm_plan* plan);
 /* tuning: Jacobi convergence threshold on max |cos(g_p,g_q)| over all column pairs, tested on the state after
  * each sweep (default 1e-11: projected X within ~2e-12 relative of LAPACK's, measured), max sweeps */
 int cuadmm_plan_set_jacobi(cuadmm_plan* plan, double threshold, int max_sweeps);
+/* Fixed-rank projection (the reference's max_dense_vector_zero_mask + get_eig_rank_mask, src/kernels/dense_scalar.cu:51-56,
+ * src/utils/get_eig_rank_mask.cu:16-38; wired but commented out in src/duo_solver.cu:843-850): with eig_rank > 0 only the
+ * eig_rank largest eigenvalues of every block survive the clamp at zero.  Blocks n <= 168 only; 0 turns it off. */
+int cuadmm_plan_set_rank_limit(cuadmm_plan* plan, int eig_rank);
+/* get_eig_rank_mask on host arrays: mask[i * mat_size + j] = 1 for the last eig_rank positions j of every block i */
+int cuadmm_eig_rank_mask(int32_t* mask, int64_t batch_size, int64_t mat_size, int64_t eig_rank);
 /* Warm start (default on; env CUADMM_JACOBI_WARM=0 turns it off): the plan keeps, per block, the
  * orthonormal eigenbasis its last projection ended in and starts the next Jacobi from it, which is
  * what makes successive ADMM iterates cheap (2-3 sweeps instead of 7-9).  The result is the same

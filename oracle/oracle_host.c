@@ -242,3 +242,11 @@ void oracle_spmv_csr(int rows, const int* rowptr, const int* colind, const doubl
         y[i] = alpha * acc + (beta == 0.0 ? 0.0 : beta * y[i]);
     }
 }
+
+/* get_eig_rank_mask (src/utils/get_eig_rank_mask.cu:16-38): zero everywhere, 1 on the last eig_rank entries of every
+ * block of mat_size (eigenvalues are ascending, so those are the eig_rank largest) */
+void oracle_eig_rank_mask(int* mask, int batch_size, int mat_size, int eig_rank) {
+    for (int i = 0; i < batch_size * mat_size; ++i) mask[i] = 0;
+    for (int i = 0; i < batch_size; ++i)
+        for (int j = 0; j < eig_rank; ++j) mask[i * mat_size + (mat_size - 1 - j)] = 1;
+}

@@ -92,6 +92,23 @@ def project_svec(blk, Xb, want_eig=False):
     return out
 
 
+def project_svec_rank(blk, Xb, eig_rank):
+    """Fixed-rank projection: the stage src/solver.cu:531-647 with max_dense_vector_zero replaced by
+    max_dense_vector_zero_mask (src/kernels/dense_scalar.cu:51-56) and the mask of get_eig_rank_mask
+    (src/utils/get_eig_rank_mask.cu:16-38): W <- max(W, 0) * mask, mask = 1 on the eig_rank largest eigenvalues
+    (the wiring is present but commented out in src/duo_solver.cu:843-850)."""
+    off = svec_offsets(blk)
+    out = np.empty_like(Xb)
+    for k, n in enumerate(blk):
+        n = int(n)
+        w, Q = eig_dsyevd(smat(Xb[off[k]:off[k + 1]], n))
+        mask = np.zeros(n)
+        mask[max(0, n - eig_rank):] = 1.0
+        wp = np.maximum(w, 0.0) * mask
+        out[off[k]:off[k + 1]] = svec((Q * wp) @ Q.T)
+    return out
+
+
 def thread_ranges(count, nthreads):
     """SDPDuoSolver's split of blocks over CPU eig threads / GPUs (src/duo_solver.cu:270-295,346-371):
     contiguous ranges; every worker gets floor(count/T), the last takes the rest, then (T > 2) the

@@ -121,3 +121,16 @@ def test_host_sparse_helpers(ohost):
     rp, ci, vv = cu.csc_to_csr_host(50, 30, M.indptr, M.indices, M.data)
     R = M.tocsr(); R.sort_indices()
     assert np.array_equal(rp, R.indptr) and np.array_equal(ci, R.indices) and np.array_equal(vv, R.data)
+
+
+def test_eig_rank_mask_golden(ohost):
+    # test/utils_test.hpp:84-99 of the reference: batch 2, size 4, rank 2
+    exp = np.array([0, 0, 1, 1, 0, 0, 1, 1], np.int32)
+    assert np.array_equal(cu.eig_rank_mask(2, 4, 2), exp)
+    m = np.zeros(8, np.int32)
+    ohost.oracle_eig_rank_mask(ip(m), 2, 4, 2)
+    assert np.array_equal(m, exp)
+    for b, n, r in [(1, 1, 0), (3, 7, 7), (5, 6, 1), (2, 9, 4)]:
+        m = np.zeros(b * n, np.int32)
+        ohost.oracle_eig_rank_mask(ip(m), b, n, r)
+        assert np.array_equal(cu.eig_rank_mask(b, n, r), m)

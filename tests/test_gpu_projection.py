@@ -285,3 +285,22 @@ def test_c3_single_block_n4000_identities():
     # BASELINE configs[2]: one dense block n = 4000 (a CPU eigendecomposition of this size is left to the bench baseline)
     blk = np.array([4000], np.int32)
     _identities(blk, random_svec(blk, seed=6))
+
+
+def test_fixed_rank_projection():
+    """max_dense_vector_zero_mask + get_eig_rank_mask (the reference's fixed-rank projection, src/duo_solver.cu:843-850):
+    only the eig_rank largest eigenvalues survive the clamp"""
+    blk = np.array([4, 9, 16, 17, 30, 33, 48, 64, 70, 100, 150], np.int32)
+    x = random_svec(blk, seed=21)
+    p = cu.Plan(blk)
+    for rank in (1, 3, 8, 200):
+        p.set_rank_limit(rank)
+        out = p.project_host(x)
+        ref = onp.project_svec_rank(blk, x, rank)
+        assert np.linalg.norm(out - ref) <= X_TOL * np.linalg.norm(ref), rank
+    p.set_rank_limit(0)
+    assert np.linalg.norm(p.project_host(x) - onp.project_svec(blk, x)) <= X_TOL * np.linalg.norm(x)
+    big = cu.Plan(np.array([200, 10], np.int32))
+    big.set_rank_limit(2)
+    with pytest.raises(cu.CuadmmError):
+        big.project_host(random_svec([200, 10], seed=1))
