@@ -444,15 +444,22 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
                                                         const int32_t* __restrict__ out_perm, int64_t perm_base,
                                                         const int* __restrict__ done_flag, int longest_last,
                                                         int64_t row0, int64_t nrows, int npush, PeerView pv,
-                                                        PeerPtrs outp, PeerPtrs scatp) {
+                                                        PeerPtrs outp, PeerPtrs scatp, int splits, double* split_part,
+                                                        unsigned int* split_count) {
     if (done_flag && *done_flag) return;
     __shared__ double part[8][9];
+    __shared__ int s_final;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned long long ep = 0;
     if (npush) ep = peer_epoch(pv);
-    // the CTAs with the longest rows go first (lower-triangular storage: the last rows), so the grid's tail
+    // `splits` CTAs share one block of 8 rows (groups of 8 consecutive chunks go round-robin over them): a rank's share of
+    // the rows is too few CTAs to pull its share of the bytes at one CTA per row block (measured 20 us for 1/8 of the
+    // rows).  The CTA that finds the other partials written adds them in split order (bit-identical on every rank).
+    const int sp = (int)(blockIdx.x % (unsigned)splits);
+    const int64_t rb = blockIdx.x / (unsigned)splits, nrb = gridDim.x / (unsigned)splits;
+    // the row blocks with the longest rows go first (lower-triangular storage: the last rows), so the grid's tail
     // wave is made of short rows
-    const int64_t cta = longest_last ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int64_t cta = longest_last ? nrb - 1 - rb : rb;
     const int64_t base = row0 + cta * 8;
     const int nr = (int)max((int64_t)0, min((int64_t)8, row0 + nrows - base));     // rows of this CTA
     double acc[8];
@@ -467,10 +474,12 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
             const int64_t j0 = tile_col[2 * t];
             const int64_t j1 = min((int64_t)tile_col[2 * t + 1], r);
             const int nch = (int)((j1 - j0 + 63) >> 6);
-            // first chunk of this run that belongs to warp w
+            // chunk with running index G = g + c belongs to warp G & 7 of split (G >> 3) % splits
+            const int g0 = g;
             int c = (w - (g & 7)) & 7;
             g += nch;
             for (; c < nch; c += 8) {
+                if (splits > 1 && (((g0 + c) >> 3) % splits) != sp) continue;
                 const int64_t j = j0 + ((int64_t)c << 6) + 2 * lane;
                 if (vec) {
                     if (j + 1 < j1) {
@@ -512,12 +521,34 @@ __global__ void __launch_bounds__(256) tail_gemv_kernel(int64_t r, const double*
     }
     __syncthreads();
     const int t = threadIdx.x;
-    if (t < 8 * max(npush, 1)) {
+    bool final_cta = true;
+    if (splits > 1) {
+        if (t < 8) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += part[k][t];
+            split_part[(rb * splits + sp) * 8 + t] = v;
+        }
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            const unsigned old = atomicAdd(split_count + rb, 1u);
+            s_final = (old == (unsigned)splits - 1u) ? 1 : 0;
+            if (s_final) { split_count[rb] = 0u; __threadfence(); }
+        }
+        __syncthreads();
+        final_cta = s_final != 0;
+    }
+    if (final_cta && t < 8 * max(npush, 1)) {
         const int q = t >> 3, rr = t & 7;
         if (rr < nr) {
             double v = 0.0;
+            if (splits > 1) {
+                for (int k = 0; k < splits; ++k) v += __ldcg(split_part + (rb * splits + k) * 8 + rr);   // split order
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v += part[k][rr];          // fixed order: identical on every rank
+                for (int k = 0; k < 8; ++k) v += part[k][rr];      // fixed order: identical on every rank
+            }
             if (npush == 0) {
                 out[base + rr] = v;
                 if (out_scatter) out_scatter[out_perm[perm_base + base + rr]] = v;
@@ -1296,6 +1327,12 @@ void cuadmm_ysolve_s::split_tail_rows(int world, int rank) {
         }
         tail_row0[k] = cut[rank]; tail_row1[k] = cut[rank + 1];
     }
+    // scratch of the split-column GEMV (allocated here: solve() may run inside a stream capture)
+    const int64_t nrb = std::max<int64_t>(1, (std::max(tail_row1[0] - tail_row0[0], tail_row1[1] - tail_row0[1]) + 7) / 8);
+    split_part.alloc(nrb * 8 * 8);
+    split_count.alloc(nrb);
+    split_count.zero();
+    CUADMM_CUDA(cudaDeviceSynchronize());
 }
 
 void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st) {
@@ -1311,6 +1348,15 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
         CUADMM_CUDA(cudaEventRecord(ev, st));
         prof_ev->push_back(ev); prof_tag->push_back(tag);
     };
+    // split-column GEMV over this rank's rows: enough CTAs per row block to fill the GPU twice
+    auto gemv_split = [&](const double* Tm, const double* in, double* out, const int32_t* tp, const int32_t* tc, int longest_last,
+                          int64_t r0, int64_t nrows_, int npush, const PeerView& pv, const PeerPtrs& outp) {
+        const int64_t nrb = std::max<int64_t>(1, (nrows_ + 7) / 8);
+        int splits = (int)std::min<int64_t>(8, std::max<int64_t>(1, (2 * 148 + nrb - 1) / nrb));
+        CUADMM_REQUIRE(split_part.n >= nrb * 8 * 8 && split_count.n >= nrb, "internal: split-column GEMV scratch too small");
+        tail_gemv_kernel<<<(unsigned)(nrb * splits), 256, 0, st>>>(n_tail, Tm, in, out, tp, tc, nullptr, nullptr, 0, done_flag,
+            longest_last, r0, nrows_, npush, pv, outp, PeerPtrs(), splits, split_part.p, split_count.p);
+    };
     if (n_tail > 0) {
         mark(20);
         // x_tail = L22^-T L22^-1 z_tail, scattered into y
@@ -1318,10 +1364,9 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
             // measurement only (CUADMM_TAIL_SIM_WORLD=W, CUADMM_TAIL_SIM_RANK=r): the rows rank r of W would compute,
             // no exchange — the result is incomplete, the timing is that of one rank's share
             const int64_t n0 = tail_row1[0] - tail_row0[0], n1 = tail_row1[1] - tail_row0[1];
-            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n0 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p,
-                tail_tcol.p, nullptr, nullptr, 0, done_flag, 1, tail_row0[0], n0, 0, PeerView(), PeerPtrs(), PeerPtrs());
-            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n1 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p,
-                tail_tcol_t.p, d_y_, perm.p, n_lead, done_flag, 0, tail_row0[1], n1, 0, PeerView(), PeerPtrs(), PeerPtrs());
+            gemv_split(tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p, tail_tcol.p, 1, tail_row0[0], n0, 0, PeerView(), PeerPtrs());
+            gemv_split(tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p, tail_tcol_t.p, 0, tail_row0[1], n1, 0, PeerView(), PeerPtrs());
+            tail_scatter_kernel<<<(int)((n_tail + 255) / 256), 256, 0, st>>>(n_tail, xv + n_lead, perm.p, n_lead, d_y_, done_flag);
         } else if (!peer || peer->world == 1) {
             const int blocks = (int)((n_tail + 7) / 8);
             // whole matrix on one GPU: row per warp streams at 69 % of the HBM peak (ncu), the split-column kernel at 55 %
@@ -1334,10 +1379,8 @@ void cuadmm_ysolve_s::solve(const double* d_rhs_, double* d_y_, cudaStream_t st)
             for (int q = 0; q < peer->world; ++q) pxt.p[q] += n_lead;
             const PeerView pv = peer->view();
             const int64_t n0 = tail_row1[0] - tail_row0[0], n1 = tail_row1[1] - tail_row0[1];
-            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n0 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p,
-                tail_tcol.p, nullptr, nullptr, 0, done_flag, 1, tail_row0[0], n0, peer->world, pv, peer_tmp, PeerPtrs());
-            tail_gemv_kernel<<<(int)std::max<int64_t>(1, (n1 + 7) / 8), 256, 0, st>>>(n_tail, tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p,
-                tail_tcol_t.p, nullptr, nullptr, 0, done_flag, 0, tail_row0[1], n1, peer->world, pv, pxt, PeerPtrs());
+            gemv_split(tail_inv.p, z.p + n_lead, tmpv, tail_tptr.p, tail_tcol.p, 1, tail_row0[0], n0, peer->world, pv, peer_tmp);
+            gemv_split(tail_inv_t.p, tmpv, xv + n_lead, tail_tptr_t.p, tail_tcol_t.p, 0, tail_row0[1], n1, peer->world, pv, pxt);
             tail_scatter_kernel<<<(int)((n_tail + 255) / 256), 256, 0, st>>>(n_tail, xv + n_lead, perm.p, n_lead, d_y_, done_flag);
         }
         CUADMM_CUDA(cudaGetLastError());

@@ -77,6 +77,8 @@ struct cuadmm_ysolve_s {
     void enable_peer(const cuadmm::PeerComm* pc, size_t off_tmp, size_t off_x);
     void split_tail_rows(int world, int rank);
     int sim_world = 0;                  // measurement only: CUADMM_TAIL_SIM_WORLD
+    cuadmm::DevBuf<double> split_part;  // split-column GEMV: partial sums per (row block, split)
+    cuadmm::DevBuf<unsigned int> split_count;
     const int* done_flag = nullptr;
     std::vector<cudaEvent_t>* prof_ev = nullptr;   // profiling (solver): events around the dense-tail stage, tags 20 / 21
     std::vector<int>* prof_tag = nullptr;
