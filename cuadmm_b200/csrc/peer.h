@@ -47,7 +47,7 @@ struct PeerComm {
     DevBuf<unsigned int> d_count;
     DevBuf<int> d_err;
     size_t off_ready = 0, off_fin = 0, off_scal_rd = 0, off_scal_rp = 0;
-    unsigned long long timeout_ns = 30ull * 1000000000ull;
+    unsigned long long timeout_ns = 120ull * 1000000000ull;   // ranks may reach their first handshake seconds apart (init skew)
 
     ~PeerComm();
     // collective: every rank calls it with the same id and arena size
