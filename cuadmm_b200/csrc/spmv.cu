@@ -17,42 +17,60 @@ namespace cuadmm {
 static constexpr int kLongRow = 256;
 static constexpr int kThreads = 256;
 
+// operands of the epilogue of row i.  They do not depend on the product, so the main loop requests them together with the
+// row pointers: issued after the dot product they were a fourth dependent round trip (40 % of the kernel's stall samples).
+struct SpmvPre { double a1, a2, a3; };
+template <int MODE>
+__device__ __forceinline__ SpmvPre spmv_prefetch(const SpmvEpilogue& e, double beta, const double* y, int64_t i) {
+    SpmvPre p = {0.0, 0.0, 0.0};
+    switch (MODE) {
+        case 0: if (beta != 0.0) p.a1 = y[i]; break;
+        case 1: p.a1 = e.aux1[i]; break;
+        case 2: p.a1 = e.aux1[i]; p.a2 = e.aux2[i]; break;
+        case 3: p.a1 = e.aux1[i]; p.a2 = e.aux2[i]; p.a3 = e.out2[i]; break;
+        case 4: p.a1 = e.aux1[i]; p.a2 = e.aux2[i]; p.a3 = e.aux3[i]; break;
+        default: break;
+    }
+    return p;
+}
+
+template <int MODE>
 __device__ __forceinline__ void spmv_store(const SpmvEpilogue& e, double alpha, double beta, double* y,
-                                           int64_t i, double r, double& acc0, double& acc1) {
-    switch (e.mode) {
+                                           int64_t i, double r, const SpmvPre& pre, double& acc0, double& acc1) {
+    switch (MODE) {
         case 0:
-            y[i] = (beta == 0.0) ? alpha * r : alpha * r + beta * y[i];
+            y[i] = (beta == 0.0) ? alpha * r : alpha * r + beta * pre.a1;
             break;
         case 1: {  // rhsy = Rp / sig - A*SmC
             const double sig = e.scal[0];
-            y[i] = e.aux1[i] / sig - r;
+            y[i] = pre.a1 / sig - r;
             break;
         }
         case 2: {  // Rd1 = At*y - C ; Xb = X + sig * Rd1
             const double sig = e.scal[0];
-            const double rd1 = r - e.aux1[i];
+            const double rd1 = r - pre.a1;
             y[i] = rd1;
-            e.out2[i] = e.aux2[i] + sig * rd1;
+            e.out2[i] = pre.a2 + sig * rd1;
             break;
         }
         case 3: {  // Rd1 = At*y - C ; Rd = Rd1 + S ; X += tau*sig*Rd ; sums |Rd|^2, <C,X>
             const double sig = e.scal[0], tau = e.scal[1];
-            const double c = e.aux1[i];
-            const double rd = (r - c) + e.aux2[i];
+            const double c = pre.a1;
+            const double rd = (r - c) + pre.a2;
             y[i] = rd;                                   // Rd
-            const double xn = e.out2[i] + (tau * sig) * rd;
+            const double xn = pre.a3 + (tau * sig) * rd;
             e.out2[i] = xn;                              // X
             acc0 = fma(rd, rd, acc0);
             acc1 = fma(c, xn, acc1);
             break;
         }
         case 4: {  // Rp = b - A*X ; sums |normA .* Rp|^2 and <b, y>
-            const double b = e.aux1[i];
+            const double b = pre.a1;
             const double rp = b - r;
             y[i] = rp;
-            const double t = e.aux2[i] * rp;             // normA[i] * Rp[i]  (bscale applied by the caller)
+            const double t = pre.a2 * rp;                // normA[i] * Rp[i]  (bscale applied by the caller)
             acc0 = fma(t, t, acc0);
-            acc1 = fma(b, e.aux3[i], acc1);              // <b, y>
+            acc1 = fma(b, pre.a3, acc1);                 // <b, y>
             break;
         }
         case 5: {  // partial row of this rank -> staging slot [rank] of the rank that reduces row i
@@ -63,11 +81,14 @@ __device__ __forceinline__ void spmv_store(const SpmvEpilogue& e, double alpha, 
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
+#ifndef CUADMM_SPMV_MINB
+#define CUADMM_SPMV_MINB 5
+#endif
+template <int G, int MODE>
+__global__ void __launch_bounds__(kThreads, CUADMM_SPMV_MINB) spmv_csr_kernel(
         int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
         const double* __restrict__ val, const double* __restrict__ x, double* y, double alpha, double beta,
-        SpmvEpilogue e, const int32_t* __restrict__ long_rows, int n_long, int main_blocks,
+        SpmvEpilogue e, const int32_t* __restrict__ long_rows, int n_long, int main_blocks, int long_thr,
         const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
     __shared__ double red[2][kThreads / 32];
@@ -81,17 +102,32 @@ __global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
         // U rows per group in flight: the loads of one row are a chain of three dependent round trips
         // (row pointer -> column/value -> x), and with ~2 entries per row there is nothing else to
         // overlap them with, so independent rows are interleaved by hand.
-        constexpr int U = 4;
+        // One lane per row (G == 1, the large operators): two rows with their epilogue operands prefetched — measured on the
+        // bench operator (scripts/stage_split_probe.py, SpMV + vector kernels per iteration): 0.146 ms as before (U = 4,
+        // operands loaded after the product), 0.119 ms so; three or four rows spill at the 48 registers that keep five
+        // CTAs per SM resident and were slower (0.126-0.135).  Lane groups (small, latency-bound operators) keep four rows
+        // and load the operands of the one storing lane late.
+        constexpr int U = (G == 1) ? 2 : 4;
+        constexpr bool PRE = (G == 1);
         for (int64_t i0 = gid; i0 < rows; i0 += ngroups * U) {
             int p0[U], p1[U];
             bool mine[U];
             double r[U];
+            SpmvPre pre[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t i = i0 + (int64_t)u * ngroups;
                 p0[u] = 0; p1[u] = 0;
-                if (i < rows) { p0[u] = rowptr[i]; p1[u] = rowptr[i + 1]; }
-                mine[u] = i < rows && p1[u] - p0[u] <= kLongRow;      // long rows belong to the warps below
+                pre[u] = SpmvPre{0.0, 0.0, 0.0};
+                if (i < rows) {
+                    p0[u] = rowptr[i]; p1[u] = rowptr[i + 1];
+                    if (PRE && sub == 0) pre[u] = spmv_prefetch<MODE>(e, beta, y, i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * ngroups;
+                mine[u] = i < rows && p1[u] - p0[u] <= long_thr;      // long rows belong to the warps below
                 if (!mine[u]) p1[u] = p0[u];
             }
 #pragma unroll
@@ -111,7 +147,10 @@ __global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t i = i0 + (int64_t)u * ngroups;
-                if (sub == 0 && mine[u]) spmv_store(e, alpha, beta, y, i, r[u], acc0, acc1);
+                if (sub == 0 && mine[u]) {
+                    if (!PRE) pre[u] = spmv_prefetch<MODE>(e, beta, y, i);
+                    spmv_store<MODE>(e, alpha, beta, y, i, r[u], pre[u], acc0, acc1);
+                }
             }
         }
     } else {
@@ -121,14 +160,16 @@ __global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
         for (int li = w; li < n_long; li += nw) {
             const int64_t i = long_rows[li];
             const int p0 = rowptr[i], p1 = rowptr[i + 1];
+            SpmvPre pre = {0.0, 0.0, 0.0};
+            if (lane == 0) pre = spmv_prefetch<MODE>(e, beta, y, i);
             double r = 0.0;
             for (int p = p0 + lane; p < p1; p += 32) r = fma(val[p], x[colind[p]], r);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-            if (lane == 0) spmv_store(e, alpha, beta, y, i, r, acc0, acc1);
+            if (lane == 0) spmv_store<MODE>(e, alpha, beta, y, i, r, pre, acc0, acc1);
         }
     }
-    if (e.partial) {
+    if ((MODE == 3 || MODE == 4) && e.partial) {
         // deterministic two-stage reduction: fixed tree inside the CTA, fixed order across CTAs later
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -149,6 +190,7 @@ __global__ void __launch_bounds__(kThreads) spmv_csr_kernel(
 struct SpmvAux {
     DevBuf<int32_t> long_rows;
     int n_long = 0;
+    int long_thr = kLongRow;       // rows with more entries than this are summed by a whole warp
     int main_blocks = 0, long_blocks = 0;
 };
 
@@ -179,10 +221,20 @@ void spmv_launch(const cuadmm_spmv_s& A_, double alpha, const double* x, double 
     const int grid = A.aux.main_blocks + A.aux.long_blocks;
     if (grid_out) *grid_out = grid;
     if (A.rows == 0 || grid == 0) return;
+#define CUADMM_SPMV_LAUNCH(G, MODE)                                                                     \
+    spmv_csr_kernel<G, MODE><<<grid, kThreads, 0, stream>>>(A.rows, A.rowptr.p, A.colind.p, A.val.p, x, y, \
+        alpha, beta, epi, A.aux.long_rows.p, A.aux.n_long, A.aux.main_blocks, A.aux.long_thr, A.done_flag)
 #define CUADMM_SPMV_CASE(G)                                                                            \
     case G:                                                                                            \
-        spmv_csr_kernel<G><<<grid, kThreads, 0, stream>>>(A.rows, A.rowptr.p, A.colind.p, A.val.p, x, y, \
-            alpha, beta, epi, A.aux.long_rows.p, A.aux.n_long, A.aux.main_blocks, A.done_flag);         \
+        switch (epi.mode) {                                                                            \
+            case 0: CUADMM_SPMV_LAUNCH(G, 0); break;                                                   \
+            case 1: CUADMM_SPMV_LAUNCH(G, 1); break;                                                   \
+            case 2: CUADMM_SPMV_LAUNCH(G, 2); break;                                                   \
+            case 3: CUADMM_SPMV_LAUNCH(G, 3); break;                                                   \
+            case 4: CUADMM_SPMV_LAUNCH(G, 4); break;                                                   \
+            case 5: CUADMM_SPMV_LAUNCH(G, 5); break;                                                   \
+            default: throw Error(CUADMM_EINVAL, "bad spmv epilogue mode");                             \
+        }                                                                                              \
         break;
     switch (A.group) {
         CUADMM_SPMV_CASE(1)
@@ -193,6 +245,7 @@ void spmv_launch(const cuadmm_spmv_s& A_, double alpha, const double* x, double 
         CUADMM_SPMV_CASE(32)
         default: throw Error(CUADMM_EINVAL, "bad spmv group size");
     }
+#undef CUADMM_SPMV_LAUNCH
 #undef CUADMM_SPMV_CASE
     CUADMM_CUDA(cudaGetLastError());
 }
@@ -220,8 +273,7 @@ cuadmm_spmv_s* spmv_create(int64_t rows, int64_t cols, int64_t nnz, const int32_
     for (int64_t i = 0; i < rows; ++i) {
         CUADMM_REQUIRE(h_rowptr[i + 1] >= h_rowptr[i], "rowptr not monotone");
         const int len = h_rowptr[i + 1] - h_rowptr[i];
-        if (len > kLongRow) longs.push_back((int32_t)i);
-        else if (len > 0) { short_nnz += len; ++short_rows; }
+        if (len > 0 && len <= kLongRow) { short_nnz += len; ++short_rows; }
     }
     for (int64_t p = 0; p < nnz; ++p) CUADMM_REQUIRE(h_colind[p] >= 0 && h_colind[p] < cols, "column index out of range");
     const double mean = short_rows ? (double)short_nnz / (double)short_rows : 1.0;
@@ -238,6 +290,15 @@ cuadmm_spmv_s* spmv_create(int64_t rows, int64_t cols, int64_t nnz, const int32_
         if (g >= 1 && g <= 32 && (g & (g - 1)) == 0) G = g;
     }
     A->group = G;
+    // one lane per row: a row of k entries is a chain of ~k/4 dependent load pairs for that lane while the 31 others idle,
+    // and the slowest lane of the last wave is the tail of the kernel (At of the bench operator: mean 1.1, max 41) — rows
+    // beyond 16 entries go to the warp-per-row part there.  Smaller matrices keep the round-1 rule (and summation order).
+    int long_thr = kLongRow;
+    if (G == 1 && rows >= 262144) long_thr = 16;
+    if (const char* e = getenv("CUADMM_SPMV_LONG")) { const int t = atoi(e); if (t >= 1 && t <= kLongRow) long_thr = t; }
+    A->aux.long_thr = long_thr;
+    for (int64_t i = 0; i < rows; ++i)
+        if (h_rowptr[i + 1] - h_rowptr[i] > long_thr) longs.push_back((int32_t)i);
     A->aux.n_long = (int)longs.size();
     if (!longs.empty()) { A->aux.long_rows.upload(longs); }
     int sm = 148;
@@ -245,20 +306,8 @@ cuadmm_spmv_s* spmv_create(int64_t rows, int64_t cols, int64_t nnz, const int32_
     const int64_t need = (rows * G + kThreads - 1) / kThreads;
     // one resident wave: the grid is capped at the CTAs per SM the kernel can keep resident (5 at 48 registers);
     // 8 per SM made 1.6 waves and cost 20-25 % (same probe).  CUADMM_SPMV_CAP overrides.
-    int cap = 5;
-    {
-        int occ = 0;
-        cudaError_t rc = cudaErrorUnknown;
-        switch (G) {
-            case 1: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<1>, kThreads, 0); break;
-            case 2: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<2>, kThreads, 0); break;
-            case 4: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<4>, kThreads, 0); break;
-            case 8: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<8>, kThreads, 0); break;
-            case 16: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<16>, kThreads, 0); break;
-            default: rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_csr_kernel<32>, kThreads, 0); break;
-        }
-        if (rc == cudaSuccess && occ >= 1) cap = occ; else cudaGetLastError();
-    }
+    const int cap_default = CUADMM_SPMV_MINB;     // every instantiation is compiled for this many resident CTAs per SM
+    int cap = cap_default;
     if (const char* e = getenv("CUADMM_SPMV_CAP")) { const int c = atoi(e); if (c >= 1 && c <= 32) cap = c; }
     A->aux.main_blocks = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)sm * cap);
     A->aux.long_blocks = longs.empty() ? 0 : (int)std::min<int64_t>(((int64_t)longs.size() + 7) / 8, (int64_t)sm);
