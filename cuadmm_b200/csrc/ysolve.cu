@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(kTriThreads) tri_subtree_kernel(const int64_t*
 #endif
 static constexpr int kPkChunk = CUADMM_PK_CHUNK;
 static constexpr int kPkRing = CUADMM_PK_RING;
-static constexpr int kPkThreads = 1024;
+#ifndef CUADMM_PK_THREADS
+#define CUADMM_PK_THREADS 1024
+#endif
+static constexpr int kPkThreads = CUADMM_PK_THREADS;
 static constexpr int kPkRecHeader = 8 + 32 + 16 + 16 + 16 + 64;
 static constexpr int kPkMaxRowEntries = 768;
 static constexpr int kPkMaxRows = 23000;
@@ -269,6 +272,58 @@ __global__ void __launch_bounds__(256) pk_gather_kernel(int64_t n_rows, int main
     }
 }
 
+// Two records of one segment at a time (they are independent: same level).  A record is a chain of dependent
+// shared-memory round trips (directory -> header -> value/index -> unknown -> shuffles), ~0.45 us for a warp that walks
+// them one by one (measured: 1,729 records in 48 segments = 47 us for the largest subtree of the bench problem);
+// interleaving two keeps twice as many loads in flight.  Every lane still adds its entries in the original order.
+__device__ __forceinline__ void pk_record2(const unsigned char* recA, const unsigned char* recB, bool hasB, int lane, double* xs) {
+    const int r = lane >> 2;
+    const bool longA = *reinterpret_cast<const int32_t*>(recA) != 0;
+    const bool longB = *reinterpret_cast<const int32_t*>(recB) != 0;
+    const int ulA = reinterpret_cast<const int32_t*>(recA + 8)[r];
+    const int ulB = hasB ? reinterpret_cast<const int32_t*>(recB + 8)[r] : -1;
+    const int voffA = reinterpret_cast<const uint16_t*>(recA + 40)[r], voffB = reinterpret_cast<const uint16_t*>(recB + 40)[r];
+    const int ioffA = reinterpret_cast<const uint16_t*>(recA + 56)[r], ioffB = reinterpret_cast<const uint16_t*>(recB + 56)[r];
+    const int lnA = reinterpret_cast<const uint16_t*>(recA + 72)[r];
+    const int lnB = hasB ? reinterpret_cast<const uint16_t*>(recB + 72)[r] : 0;
+    const double invdA = reinterpret_cast<const double*>(recA + 88)[r], invdB = reinterpret_cast<const double*>(recB + 88)[r];
+    const int jA = longA ? lane : (lane & 3), jB = longB ? lane : (lane & 3);
+    const int stepA = longA ? 32 : 4, stepB = longB ? 32 : 4;
+    const double* valA = reinterpret_cast<const double*>(recA) + voffA;
+    const double* valB = reinterpret_cast<const double*>(recB) + voffB;
+    const uint16_t* idxA = reinterpret_cast<const uint16_t*>(recA) + ioffA;
+    const uint16_t* idxB = reinterpret_cast<const uint16_t*>(recB) + ioffB;
+    const double curA = ulA >= 0 ? xs[ulA] : 0.0;
+    const double curB = ulB >= 0 ? xs[ulB] : 0.0;
+    double accA = 0.0, accB = 0.0;
+    int kA = jA, kB = jB;
+    while (kA < lnA || kB < lnB) {
+        const bool a = kA < lnA, b = kB < lnB;
+        double va = 0.0, vb = 0.0;
+        int ia = 0, ib = 0;
+        if (a) { va = valA[kA]; ia = idxA[kA]; }
+        if (b) { vb = valB[kB]; ib = idxB[kB]; }
+        const double xa = xs[ia], xb = xs[ib];
+        if (a) accA = fma(va, xa, accA);
+        if (b) accB = fma(vb, xb, accB);
+        kA += stepA; kB += stepB;
+    }
+    accA += __shfl_xor_sync(0xffffffffu, accA, 1);
+    accB += __shfl_xor_sync(0xffffffffu, accB, 1);
+    accA += __shfl_xor_sync(0xffffffffu, accA, 2);
+    accB += __shfl_xor_sync(0xffffffffu, accB, 2);
+    if (longA || longB) {                       // warp-uniform; a short record's extra sums are discarded (only j == 0 stores)
+        double tA = accA, tB = accB;
+        tA += __shfl_xor_sync(0xffffffffu, tA, 4);  tB += __shfl_xor_sync(0xffffffffu, tB, 4);
+        tA += __shfl_xor_sync(0xffffffffu, tA, 8);  tB += __shfl_xor_sync(0xffffffffu, tB, 8);
+        tA += __shfl_xor_sync(0xffffffffu, tA, 16); tB += __shfl_xor_sync(0xffffffffu, tB, 16);
+        if (longA) accA = tA;
+        if (longB) accB = tB;
+    }
+    if (ulA >= 0 && jA == 0) xs[ulA] = (curA - accA) * invdA;
+    if (ulB >= 0 && jB == 0) xs[ulB] = (curB - accB) * invdB;
+}
+
 // walk the segments of one chunk (resident in shared memory) with NW warps; WARP = the chunk belongs to one warp
 template <int NW, bool WARP>
 __device__ __forceinline__ void pk_chunk(const unsigned char* chunk, int lane, int warp, double* xs) {
@@ -279,13 +334,16 @@ __device__ __forceinline__ void pk_chunk(const unsigned char* chunk, int lane, i
     int sb = 0;
     for (int g = 0; g < nseg; ++g) {
         const int se = seg_end[g];
-        for (int sl = sb + warp; sl < se; sl += NW) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
+        int sl = sb + warp;
+        for (; sl + NW < se; sl += 2 * NW)
+            pk_record2(chunk + 8 * (int)rec_off[sl], chunk + 8 * (int)rec_off[sl + NW], true, lane, xs);
+        if (sl < se) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
         if constexpr (WARP) __syncwarp(); else __syncthreads();
         sb = se;
     }
 }
 
-__global__ void __launch_bounds__(kPkThreads) tri_packed_kernel(const int64_t* __restrict__ chunk_off,
+__global__ void __launch_bounds__(kPkThreads, 1) tri_packed_kernel(const int64_t* __restrict__ chunk_off,
         const int64_t* __restrict__ row_off, const unsigned char* __restrict__ stream, const int32_t* __restrict__ prow_u,
         const int32_t* __restrict__ prow_out, const double* __restrict__ w, double* x, double* out_scatter,
         const int* __restrict__ done_flag, long long* __restrict__ timeline) {
@@ -876,6 +934,18 @@ static void pack_subtrees(const HostSweep& H, TriSweep& S, const std::vector<std
         for (int l = 0; l < new_depth; ++l) {
             std::vector<const PkRow*> longs, shorts;
             for (const PkRow& r : lv[l]) ((int)r.idx.size() > kLongRowNnz ? longs : shorts).push_back(&r);
+            if (nr0 > kPkWarpRows && !shorts.empty()) {
+                // CTA subtree, thin level (fewer records than the 32 warps of the CTA): its time is the longest row's chain
+                // of dependent index -> unknown loads, 4 lanes per row = up to 6 rounds.  Warps are idle anyway, so the
+                // longest rows get a whole warp each (one round) as long as every record still has its own warp.
+                constexpr int kWarps = kPkThreads / 32;
+                std::stable_sort(shorts.begin(), shorts.end(), [](const PkRow* a, const PkRow* b) { return a->idx.size() > b->idx.size(); });
+                size_t promote = 0;
+                while (promote < shorts.size() && shorts[promote]->idx.size() > 4 &&
+                       longs.size() + promote + 1 + (shorts.size() - promote - 1 + 7) / 8 <= (size_t)kWarps) ++promote;
+                longs.insert(longs.end(), shorts.begin(), shorts.begin() + promote);
+                shorts.erase(shorts.begin(), shorts.begin() + promote);
+            }
             std::stable_sort(longs.begin(), longs.end(), [](const PkRow* a, const PkRow* b) { return a->idx.size() > b->idx.size(); });
             bool first = true;
             for (const PkRow* r : longs) { add_record(make_record(&r, 1, true), first); first = false; }
