@@ -215,11 +215,15 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
     mat_sync<WARP>();
     // Frobenius norm of the 2^-ex prescaled block (no over/underflow for any finite input)
     double f2 = 0.0;
-    for (int e = tid; e < n * n; e += NT) {
-        const int c = e / n, r = e - c * n;
+    // (r, c) of entry e = tid + k NT advanced incrementally: an integer division per entry was 8 % of the zero-sweep time
+    const int e_dc = NT / n, e_dr = NT - e_dc * n;
+    const int e_c0 = tid / n, e_r0 = tid - e_c0 * n;
+    for (int c = e_c0, r = e_r0; c < n;) {
         const double v = ldexp(G[r + c * ld], -ex);
         G[r + c * ld] = v;
         f2 = fma(v, v, f2);
+        r += e_dr; c += e_dc;
+        if (r >= n) { r -= n; ++c; }
     }
     f2 = mat_sum<NT, WARP>(f2, red, tid);
     const double sp = sqrt(f2);              // ||A||_F * 2^-ex
@@ -242,10 +246,11 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
     }
     const double inv_s = 1.0 / sp;
     // G <- A / ||A||_F + I
-    for (int e = tid; e < n * n; e += NT) {
-        const int c = e / n, r = e - c * n;
+    for (int c = e_c0, r = e_r0; c < n;) {
         const double v = G[r + c * ld] * inv_s;
         G[r + c * ld] = (r == c) ? v + 1.0 : v;
+        r += e_dr; c += e_dc;
+        if (r >= n) { r -= n; ++c; }
     }
     mat_sync<WARP>();
 
@@ -448,52 +453,86 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
     mat_sync<WARP>();
     const int kpos = pos[n];
     // h_j = sqrt(w_j) g_j for the positive columns
-    for (int e = tid; e < kpos * n; e += NT) {
-        const int jj = e / n, r = e - jj * n;
+    for (int jj = e_c0, r = e_r0; jj < kpos;) {
         const int j = pos[jj];
         G[r + j * ld] *= w[j];
+        r += e_dr; jj += e_dc;
+        if (r >= n) { r -= n; ++jj; }
     }
     mat_sync<WARP>();
 
     // ---- rebuild + smat -> svec (matrices_to_vector), optional fused S / SmC ----
+    // Pi_+ = s H H^T with H = the kpos scaled positive columns: 8 x 8 output tiles on the FP64 tensor cores
+    // (mma.sync.m8n8k4: A = rows of H, B = rows of H again, read through pos[]), upper tile triangle only.  A unit of work
+    // is one 8-column block and up to four 8-row blocks above it (they share the B fragment); the accumulator layout
+    // (row = lane / 4, columns 2 (lane % 4) + {0, 1}) gives the svec index c (c + 1) / 2 + r directly and makes the 8
+    // lanes of a column touch 64 contiguous bytes of the svec vectors.  (The scalar loop this replaces — two shared
+    // loads per FMA and a triangular un-ranking per entry — was 20 % of the kernel's time at zero sweeps.)
     double sig = 1.0;
     if (a.epi.X) sig = *a.epi.sig_ptr;
-    for (int idx0 = tid; idx0 < ntri; idx0 += NT * 2) {
-        // two entries per pass; the epilogue's global operands are requested before the accumulation they do not depend on
-        const int idx1 = idx0 + NT;
-        const bool two = idx1 < ntri;
-        double xv0 = 0.0, rd0 = 0.0, cd0 = 0.0, xv1 = 0.0, rd1 = 0.0, cd1 = 0.0;
-        if (a.epi.X) {
-            const int64_t g0 = d.svec_off + idx0;
-            xv0 = __ldg(a.epi.X + g0); rd0 = __ldg(a.epi.Rd1 + g0); cd0 = __ldg(a.epi.Cd + g0);
-            if (two) { const int64_t g1 = d.svec_off + idx1; xv1 = __ldg(a.epi.X + g1); rd1 = __ldg(a.epi.Rd1 + g1); cd1 = __ldg(a.epi.Cd + g1); }
-        }
-        int r0, c0, r1 = 0, c1 = 0;
-        tri_unrank(idx0, r0, c0);
-        if (two) tri_unrank(idx1, r1, c1);
-        double acc0 = 0.0, acc1 = 0.0;
-        for (int jj = 0; jj < kpos; ++jj) {
-            const double* Gj = G + pos[jj] * ld;
-            acc0 = fma(Gj[r0], Gj[c0], acc0);
-            acc1 = fma(Gj[r1], Gj[c1], acc1);
-        }
-        acc0 *= s_true; acc1 *= s_true;
-        const double out0 = (r0 == c0) ? acc0 : acc0 * CUADMM_SQRT2;
-        xout[idx0] = out0;
-        if (a.epi.X) {
-            const int64_t g0 = d.svec_off + idx0;
-            const double Sv = (out0 - xv0) / sig - rd0;
-            a.epi.S[g0] = Sv;
-            a.epi.SmC[g0] = Sv - cd0;
-        }
-        if (two) {
-            const double out1 = (r1 == c1) ? acc1 : acc1 * CUADMM_SQRT2;
-            xout[idx1] = out1;
-            if (a.epi.X) {
-                const int64_t g1 = d.svec_off + idx1;
-                const double Sv = (out1 - xv1) / sig - rd1;
-                a.epi.S[g1] = Sv;
-                a.epi.SmC[g1] = Sv - cd1;
+    {
+        constexpr int NWARP = WARP ? 1 : NT / 32;
+        const int wid = WARP ? 0 : (tid >> 5);
+        const int l32 = tid & 31;
+        const int fr = l32 >> 2, fk = l32 & 3;
+        const int T8 = (n + 7) >> 3;
+        const int nkk = (kpos + 3) >> 2;
+        int unit = 0;
+        for (int C = 0; C < T8; ++C) {
+            for (int R0 = 0; R0 <= C; R0 += 4, ++unit) {
+                if (unit % NWARP != wid) continue;
+                const int nR = min(4, C + 1 - R0);
+                // outputs of this lane: (r_t, c_h) = (8 (R0 + t) + fr, 8 C + 2 fk + h); epilogue operands requested first
+                double xv[4][2], rd[4][2], cd[4][2];
+                if (a.epi.X) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = 8 * (R0 + t) + fr, c = 8 * C + 2 * fk + h;
+                            xv[t][h] = 0.0; rd[t][h] = 0.0; cd[t][h] = 0.0;
+                            if (t < nR && r <= c && c < n) {
+                                const int64_t g = d.svec_off + (int64_t)c * (c + 1) / 2 + r;
+                                xv[t][h] = __ldg(a.epi.X + g); rd[t][h] = __ldg(a.epi.Rd1 + g); cd[t][h] = __ldg(a.epi.Cd + g);
+                            }
+                        }
+                }
+                double acc[4][2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+                const int brow = 8 * C + fr;
+                for (int kk = 0; kk < nkk; ++kk) {
+                    const int k = 4 * kk + fk;
+                    const bool kv = k < kpos;
+                    const double* Gk = G + (kv ? pos[k] : 0) * ld;
+                    const double b = (kv && brow < n) ? Gk[brow] : 0.0;
+                    double av[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int r = 8 * (R0 + t) + fr;
+                        av[t] = (kv && t < nR && r < n) ? Gk[r] : 0.0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) jacobi_dmma(acc[t][0], acc[t][1], av[t], b);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = 8 * (R0 + t) + fr, c = 8 * C + 2 * fk + h;
+                        if (t < nR && r <= c && c < n) {
+                            const int idx = c * (c + 1) / 2 + r;
+                            const double v = acc[t][h] * s_true;
+                            const double out = (r == c) ? v : v * CUADMM_SQRT2;
+                            xout[idx] = out;
+                            if (a.epi.X) {
+                                const int64_t g = d.svec_off + idx;
+                                const double Sv = (out - xv[t][h]) / sig - rd[t][h];
+                                a.epi.S[g] = Sv;
+                                a.epi.SmC[g] = Sv - cd[t][h];
+                            }
+                        }
+                    }
             }
         }
     }
