@@ -32,8 +32,24 @@ namespace cuadmm {
 #ifndef CUADMM_SG_STAGES
 #define CUADMM_SG_STAGES 4
 #endif
-static constexpr int SG_M = 128, SG_N = 128, SG_K = CUADMM_SG_K, SG_PAD = 4, SG_THREADS = 256, SG_STAGES = CUADMM_SG_STAGES;
-static constexpr size_t SG_SMEM = sizeof(double) * SG_STAGES * SG_K * ((SG_M + SG_PAD) + (SG_N + SG_PAD));
+// Two tile shapes, one kernel template: WM x WN warps of 32 x 64 each.
+//   <2, 1>:  64 x  64 tile,  64 threads, 3 stages ( 52 KB): four CTAs per SM.  Co-resident CTAs overlap one tile's prologue
+//            and epilogue with the others' main loops and the finer tiles waste less on the padded edge and the diagonal:
+//            measured against the 128-tile shape (scripts/dense_probe.py, ms per projection): 64 x n=200 4.61 -> 4.04,
+//            32 x 320 5.66 -> 3.25, 16 x 500 7.33 -> 4.19, 16 x 800 22.2 -> 18.2, 4 x 1200 14.8 -> 14.6, n = 2000 and
+//            n = 4000 equal.  Used up to kSmallTileMax;
+//   <4, 2>: 128 x 128 tile, 256 threads, 4 stages (135 KB): one CTA per SM, half the operand traffic per flop — kept for
+//            the blocks whose operands no longer fit the L2 (n > 2048).
+static constexpr int SG_K = CUADMM_SG_K, SG_PAD = 4, SG_STAGES = CUADMM_SG_STAGES, SG_STAGES_SMALL = 3;
+template <int WM, int WN> struct SgShape {
+    static constexpr int TM = 32 * WM, TN = 64 * WN, THREADS = 32 * WM * WN;
+    static constexpr int STAGES = (WM * WN >= 8) ? SG_STAGES : SG_STAGES_SMALL;
+    static constexpr size_t SMEM = sizeof(double) * STAGES * SG_K * ((TM + SG_PAD) + (TN + SG_PAD));
+    static_assert(TM == TN, "symmetric products need square tiles");
+};
+using SgBig = SgShape<4, 2>;
+using SgSmall = SgShape<2, 1>;
+static constexpr int kSmallTileMax = 2048;
 
 struct DenseDesc {
     int64_t off;        // element offset of the block in every n x n pool
@@ -86,17 +102,24 @@ __device__ __forceinline__ bool sign_frozen(const double* __restrict__ res, int 
     return false;
 }
 
-__global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* __restrict__ desc,
+// work[i] = (block, linear lower-triangular tile index): one CTA per entry
+template <int WM, int WN>
+__global__ void __launch_bounds__(SgShape<WM, WN>::THREADS) sym_gemm_kernel(const DenseDesc* __restrict__ desc,
+        const int2* __restrict__ work,
         const double* __restrict__ Ap, const double* __restrict__ Bp, double* Cp, const double* __restrict__ Dp,
         double alpha, double dshift, double gamma, const int* __restrict__ done_flag,
         SignStep st, double* res_all, int res_stride, double tolsq) {
+    using Sh = SgShape<WM, WN>;
+    constexpr int SG_M = Sh::TM, SG_N = Sh::TN, SG_THREADS = Sh::THREADS, STAGES = Sh::STAGES;
     if (done_flag && *done_flag) return;
     const int mode = st.mode;
-    double* res = res_all ? res_all + (size_t)blockIdx.y * res_stride : nullptr;
+    const int2 wk = work[blockIdx.x];
+    const int blk_id = wk.x;
+    double* res = res_all ? res_all + (size_t)blk_id * res_stride : nullptr;
     bool frozen = false;
     if (mode != 0) frozen = sign_frozen(res, st.k, tolsq, st.stag_from);
     if ((mode == 1 || mode == 3) && frozen) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) res[st.k] = res[st.k - 1];
+        if (wk.y == 0 && threadIdx.x == 0) res[st.k] = res[st.k - 1];
         return;
     }
     if (mode == 2 && frozen) return;
@@ -112,13 +135,11 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
     }
     extern __shared__ double sg_smem[];
     double (*As)[SG_K][SG_M + SG_PAD] = reinterpret_cast<double (*)[SG_K][SG_M + SG_PAD]>(sg_smem);
-    double (*Bs)[SG_K][SG_N + SG_PAD] = reinterpret_cast<double (*)[SG_K][SG_N + SG_PAD]>(sg_smem + SG_STAGES * SG_K * (SG_M + SG_PAD));
-    const DenseDesc d = desc[blockIdx.y];
+    double (*Bs)[SG_K][SG_N + SG_PAD] = reinterpret_cast<double (*)[SG_K][SG_N + SG_PAD]>(sg_smem + STAGES * SG_K * (SG_M + SG_PAD));
+    const DenseDesc d = desc[blk_id];
     const int n = d.n;
-    const int T = (n + SG_M - 1) / SG_M;
     // linear lower-triangular tile index -> (ti, tj), ti >= tj
-    const int p = blockIdx.x;
-    if (p >= T * (T + 1) / 2) return;
+    const int p = wk.y;
     int ti = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
     while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
     while (ti * (ti + 1) / 2 > p) --ti;
@@ -129,7 +150,7 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
     const int64_t ld = n;
     const int m0 = ti * SG_M, n0 = tj * SG_N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+    const int wm = (warp % WM) * 32, wn = (warp / WM) * 64;
 
     if (mode == 4 && frozen) {
         // converged block: X_{k+1} = X_k (tile copy, mirrored like the product)
@@ -158,9 +179,9 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
             // A tile 128 (m) x 16 (k): element (mm, kk) at A[m0+mm + (k0+kk) ld] (contiguous along m); same for B
             // through its transpose: B(kk, nn) = B(nn, kk) at B[n0+nn + (k0+kk) ld]
 #pragma unroll
-            for (int t = 0; t < SG_K / 4; ++t) {
-                const int e = tid + t * SG_THREADS;            // 64 16-byte chunks per k-row and operand
-                const int mm = (e & 63) * 2, kk = e >> 6;
+            for (int t = 0; t < (SG_K * SG_M / 2) / SG_THREADS; ++t) {
+                const int e = tid + t * SG_THREADS;            // SG_M / 2 16-byte chunks per k-row and operand
+                const int mm = (e % (SG_M / 2)) * 2, kk = e / (SG_M / 2);
                 const int gk = k0 + kk;
                 const int gm = m0 + mm, gn = n0 + mm;
                 const bool oka = gm < n && gk < n, okb = gn < n && gk < n;
@@ -169,9 +190,9 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
             }
         } else {
 #pragma unroll
-            for (int t = 0; t < SG_K / 2; ++t) {
+            for (int t = 0; t < (SG_K * SG_M) / SG_THREADS; ++t) {
                 const int e = tid + t * SG_THREADS;
-                const int mm = e & 127, kk = e >> 7;
+                const int mm = e % SG_M, kk = e / SG_M;
                 const int gk = k0 + kk;
                 const int gm = m0 + mm, gn = n0 + mm;
                 const bool oka = gm < n && gk < n, okb = gn < n && gk < n;
@@ -183,15 +204,15 @@ __global__ void __launch_bounds__(SG_THREADS) sym_gemm_kernel(const DenseDesc* _
 
     const int nk = (n + SG_K - 1) / SG_K;
 #pragma unroll
-    for (int s = 0; s < SG_STAGES - 1; ++s) {
+    for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) load_tiles(s, s * SG_K);
         cp_async_commit();
     }
     for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt % SG_STAGES;
-        cp_async_wait<SG_STAGES - 2>();        // tile kt has landed (this thread's copies) ...
+        const int buf = kt % STAGES;
+        cp_async_wait<STAGES - 2>();           // tile kt has landed (this thread's copies) ...
         __syncthreads();                       // ... and everybody's; everybody is also done with tile kt-1's buffer
-        if (kt + SG_STAGES - 1 < nk) load_tiles((kt + SG_STAGES - 1) % SG_STAGES, (kt + SG_STAGES - 1) * SG_K);
+        if (kt + STAGES - 1 < nk) load_tiles((kt + STAGES - 1) % STAGES, (kt + STAGES - 1) * SG_K);
         cp_async_commit();
 #pragma unroll
         for (int kk = 0; kk < SG_K; kk += 4) {
@@ -323,8 +344,46 @@ struct DensePart {
     DevBuf<double> fro2;
     DevBuf<double> res;             // (kMaxNsSteps + 1) residual slots per block, block-major
     int nmax = 0;
-    size_t smem = 0;
+    DevBuf<int2> work_big, work_small;   // (block, tile) lists of the two tile shapes
+    int n_big = 0, n_small = 0;
 };
+
+// lower-triangular tile lists of a set of blocks: blocks up to small_max use the 64-tile shape
+static void sym_work_lists(const std::vector<DenseDesc>& desc, int small_max, std::vector<int2>& big, std::vector<int2>& small) {
+    for (int b = 0; b < (int)desc.size(); ++b) {
+        const bool sm = desc[b].n <= small_max;
+        const int tile = sm ? SgSmall::TM : SgBig::TM;
+        const int T = (desc[b].n + tile - 1) / tile;
+        for (int p = 0; p < T * (T + 1) / 2; ++p) (sm ? small : big).push_back(make_int2(b, p));
+    }
+}
+
+static int small_tile_max() {
+    int v = kSmallTileMax;
+    if (const char* e = getenv("CUADMM_SG_SMALL_MAX")) v = atoi(e);     // tuning: 0 = every block on 128-tiles
+    return v;
+}
+
+static void sym_gemm_attrs() {
+    CUADMM_CUDA(cudaFuncSetAttribute((const void*)sym_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SgBig::SMEM));
+    CUADMM_CUDA(cudaFuncSetAttribute((const void*)sym_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SgSmall::SMEM));
+}
+
+// one grouped product over both tile lists; returns the number of launches
+static int sym_gemm_launch(const DenseDesc* desc, const int2* wbig, int nbig, const int2* wsmall, int nsmall, const double* A,
+                           const double* B, double* C, const double* Dm, double alpha, double dshift, double gamma,
+                           const int* done_flag, const SignStep& g, double* res, int rs, double tolsq, cudaStream_t st) {
+    int launches = 0;
+    if (nbig) {
+        sym_gemm_kernel<4, 2><<<nbig, SgBig::THREADS, SgBig::SMEM, st>>>(desc, wbig, A, B, C, Dm, alpha, dshift, gamma, done_flag, g, res, rs, tolsq);
+        ++launches;
+    }
+    if (nsmall) {
+        sym_gemm_kernel<2, 1><<<nsmall, SgSmall::THREADS, SgSmall::SMEM, st>>>(desc, wsmall, A, B, C, Dm, alpha, dshift, gamma, done_flag, g, res, rs, tolsq);
+        ++launches;
+    }
+    return launches;
+}
 
 }  // namespace cuadmm
 
@@ -351,8 +410,12 @@ cuadmm::DensePart* dense_part_create(int device, const std::vector<int32_t>& blk
     D->A.alloc(off); D->X.alloc(off); D->Y.alloc(off); D->Z.alloc(off);
     D->fro2.alloc((int64_t)which.size());
     D->res.alloc((int64_t)which.size() * (kMaxNsSteps + 1));
-    D->smem = SG_SMEM;
-    CUADMM_CUDA(cudaFuncSetAttribute((const void*)sym_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem));
+    std::vector<int2> big, small;
+    sym_work_lists(D->h_desc, small_tile_max(), big, small);
+    D->n_big = (int)big.size(); D->n_small = (int)small.size();
+    if (!big.empty()) D->work_big.upload(big);
+    if (!small.empty()) D->work_small.upload(small);
+    sym_gemm_attrs();
     return D.release();
 }
 
@@ -368,8 +431,6 @@ int dense_part_project(cuadmm::DensePart* D, const double* Xb, double* Xproj, cu
     dim3 gs(std::min((int)(((int64_t)D->nmax * D->nmax + 255) / 256), 2048), nb);
     dense_scale_kernel<<<gs, 256, 0, st>>>(D->d_desc.p, D->A.p, D->X.p, D->fro2.p, done_flag);
     launches += 2;
-    const int T = (D->nmax + SG_M - 1) / SG_M;
-    dim3 gg(T * (T + 1) / 2, nb);
     double* X = D->X.p; double* Y = D->Y.p; double* Z = D->Z.p;
     const int rs = kMaxNsSteps + 1;
     CUADMM_CUDA(cudaMemsetAsync(D->res.p, 0, sizeof(double) * (size_t)nb * rs, st));
@@ -379,21 +440,24 @@ int dense_part_project(cuadmm::DensePart* D, const double* Xb, double* Xproj, cu
         // Y = X X (+ residual of X_k; step 0: ||X_0^2||_F^2, the scale) ; Z = c Y Y + b Y ; Y = X Z + a X ; swap(X, Y)
         SignStep g1{s0 ? 3 : 1, k, 0, 0, kSignTable + 1}, g2{2, k, s0 ? 4 : 0, s0 ? 2 : 0, kSignTable + 1},
                  g3{4, k, s0 ? 1 : 0, s0 ? 1 : 0, kSignTable + 1};
-        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, X, Y, nullptr, 1.0, 0.0, 0.0, done_flag, g1, D->res.p, rs, kNsTolSq);
-        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, Y, Y, Z, Y, co[2], 0.0, co[1], done_flag, g2, D->res.p, rs, kNsTolSq);
-        sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, Z, Y, X, 1.0, 0.0, co[0], done_flag, g3, D->res.p, rs, kNsTolSq);
+        auto prod = [&](const double* A_, const double* B_, double* C_, const double* D_, double al, double ga, const SignStep& g) {
+            launches += sym_gemm_launch(D->d_desc.p, D->work_big.p, D->n_big, D->work_small.p, D->n_small, A_, B_, C_, D_, al, 0.0, ga,
+                                        done_flag, g, D->res.p, rs, kNsTolSq, st);
+        };
+        prod(X, X, Y, nullptr, 1.0, 0.0, g1);
+        prod(Y, Y, Z, Y, co[2], co[1], g2);
+        prod(X, Z, Y, X, 1.0, co[0], g3);
         std::swap(X, Y);
-        launches += 3;
     }
     // P = (U A + A) / 2 with U = sign(A) in X
     SignStep plain{0, 0, 0, 0, 0};
-    sym_gemm_kernel<<<gg, SG_THREADS, D->smem, st>>>(D->d_desc.p, X, D->A.p, Y, D->A.p, 0.5, 0.0, 0.5, done_flag,
-                                                      plain, nullptr, rs, 0.0);
+    launches += sym_gemm_launch(D->d_desc.p, D->work_big.p, D->n_big, D->work_small.p, D->n_small, X, D->A.p, Y, D->A.p, 0.5, 0.0, 0.5,
+                                done_flag, plain, nullptr, rs, 0.0, st);
     double* Pout = Y;
     ProjEpilogue e;
     if (epi) e = *epi; else { e.X = nullptr; e.Rd1 = nullptr; e.Cd = nullptr; e.S = nullptr; e.SmC = nullptr; e.sig_ptr = nullptr; }
     dense_store_kernel<<<gl, 256, 0, st>>>(D->d_desc.p, Pout, Xproj, e, done_flag);
-    launches += 2;
+    launches += 1;
     CUADMM_CUDA(cudaGetLastError());
     return launches;
 }
@@ -407,12 +471,15 @@ extern "C" int cuadmm_debug_sym_gemm(int n, const double* hA, const double* hB, 
         DenseDesc d; d.off = 0; d.svec_off = 0; d.n = n; d.pad = 0;
         DevBuf<DenseDesc> dd(1);
         CUADMM_CUDA(cudaMemcpy(dd.p, &d, sizeof d, cudaMemcpyHostToDevice));
-        const size_t smem = SG_SMEM;
-        CUADMM_CUDA(cudaFuncSetAttribute((const void*)sym_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int T = (n + SG_M - 1) / SG_M;
+        sym_gemm_attrs();
+        std::vector<int2> big, small;
+        sym_work_lists(std::vector<DenseDesc>(1, d), small_tile_max(), big, small);
+        DevBuf<int2> wb, ws;
+        if (!big.empty()) wb.upload(big);
+        if (!small.empty()) ws.upload(small);
         SignStep plain{0, 0, 0, 0, 0};
-        sym_gemm_kernel<<<dim3(T * (T + 1) / 2, 1), SG_THREADS, smem>>>(dd.p, A.p, B.p, C.p, nullptr, alpha, dshift, 0.0, nullptr,
-                                                                        plain, nullptr, 1, 0.0);
+        sym_gemm_launch(dd.p, wb.p, (int)big.size(), ws.p, (int)small.size(), A.p, B.p, C.p, nullptr, alpha, dshift, 0.0, nullptr,
+                        plain, nullptr, 1, 0.0, 0);
         CUADMM_CUDA(cudaGetLastError());
         C.download(hC, nn);
         CUADMM_CUDA(cudaDeviceSynchronize());
