@@ -70,6 +70,18 @@ def test_large_blocks_dense_sign_path():
     _check([1000], random_svec([1000], seed=3))
 
 
+def test_large_blocks_both_tile_shapes_in_one_plan(monkeypatch):
+    # blocks up to n = 2048 run on 64 x 64 tiles, larger ones on 128 x 128 tiles (two work lists per product, csrc/dense_proj.cu);
+    # a plan that holds both, plus shared-memory Jacobi blocks, against LAPACK — and the same blocks with the threshold moved
+    blk = [2100, 300, 40, 700]
+    x = random_svec(blk, seed=7)
+    out, _ = _check(blk, x)
+    for thr in ("0", "100000"):              # everything on 128-tiles / everything on 64-tiles
+        monkeypatch.setenv("CUADMM_SG_SMALL_MAX", thr)
+        alt = cu.Plan(np.asarray(blk, np.int32), device=0).project_host(x)
+        assert np.linalg.norm(alt - out) <= 1e-12 * np.linalg.norm(out)
+
+
 def test_large_blocks_degenerate_spectra():
     rng = np.random.default_rng(5)
     n = 300

@@ -63,3 +63,24 @@ def test_linearity_at_size():
     y = A.apply_host(x1) + 2 * A.apply_host(x2)
     assert np.allclose(y12, y, rtol=0, atol=1e-12 * np.abs(y).max())
     assert np.allclose(A.apply_host(x1), M @ x1, rtol=0, atol=1e-13 * np.abs(M @ x1).max())
+
+
+def test_large_short_row_operator_with_medium_rows():
+    """the bench operator's regime: >= 262,144 rows with ~1-2 entries each run one lane per row (two rows in flight, epilogue
+    operands prefetched); rows of 17..256 entries take the warp-per-row part there (threshold 16), longer ones always"""
+    rows, cols = 300000, 150000
+    rng = np.random.default_rng(5)
+    nnz = 450000
+    r = rng.integers(0, rows, nnz); c = rng.integers(0, cols, nnz); v = rng.standard_normal(nnz)
+    for k in (17, 40, 200, 256, 257, 1000):          # a few medium / long rows
+        row = rng.integers(0, rows)
+        r = np.concatenate([r, np.full(k, row)]); c = np.concatenate([c, rng.choice(cols, k, replace=False)])
+        v = np.concatenate([v, rng.standard_normal(k)])
+    M = sp.csr_matrix((v, (r, c)), shape=(rows, cols)); M.sum_duplicates(); M.sort_indices()
+    A = cu.SpMV(rows, cols, M.indptr, M.indices, M.data)
+    x = rng.standard_normal(cols); y0 = rng.standard_normal(rows)
+    scale = (abs(M) @ abs(x)) + 1e-300
+    y = A.apply_host(x, alpha=1.0, beta=0.0)
+    assert np.max(np.abs(y - M @ x) / scale) < 1e-14
+    y = A.apply_host(x, alpha=-0.5, beta=2.0, y=y0)          # beta != 0: the prefetched operand is y itself
+    assert np.max(np.abs(y - (-0.5 * (M @ x) + 2 * y0)) / (0.5 * scale + 2 * abs(y0))) < 1e-14
