@@ -335,9 +335,11 @@ __device__ __forceinline__ void pk_chunk(const unsigned char* chunk, int lane, i
     for (int g = 0; g < nseg; ++g) {
         const int se = seg_end[g];
         int sl = sb + warp;
-        for (; sl + NW < se; sl += 2 * NW)
-            pk_record2(chunk + 8 * (int)rec_off[sl], chunk + 8 * (int)rec_off[sl + NW], true, lane, xs);
-        if (sl < se) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
+        if constexpr (!WARP) {      // (the one-warp subtrees have 1-2 records per level: pairing buys nothing there and costs registers)
+            for (; sl + NW < se; sl += 2 * NW)
+                pk_record2(chunk + 8 * (int)rec_off[sl], chunk + 8 * (int)rec_off[sl + NW], true, lane, xs);
+        }
+        for (; sl < se; sl += NW) pk_record(chunk + 8 * (int)rec_off[sl], lane, xs);
         if constexpr (WARP) __syncwarp(); else __syncthreads();
         sb = se;
     }
@@ -397,7 +399,7 @@ static constexpr int kPkWarpBlob = 2048;      // bytes; bigger subtrees go to tr
 static constexpr int kPkWarpRows = 32;
 static constexpr int kPkWarpThreads = 256;
 
-__global__ void __launch_bounds__(kPkWarpThreads) tri_packed_warp_kernel(int64_t count, const int64_t* __restrict__ blob_off,
+__global__ void __launch_bounds__(kPkWarpThreads, 5) tri_packed_warp_kernel(int64_t count, const int64_t* __restrict__ blob_off,
         const int64_t* __restrict__ row_off, const uint4* __restrict__ blobs, const int32_t* __restrict__ prow_u,
         const int32_t* __restrict__ prow_out, const double* __restrict__ w, double* x, double* out_scatter,
         const int* __restrict__ done_flag) {
