@@ -755,6 +755,7 @@ static const Variant kVariants[] = {
     /*13*/ CUADMM_VARIANT(352, 8, 21, false),
     /*14*/ CUADMM_VARIANT(256, 8, 4, true),
     /*15*/ CUADMM_VARIANT(128, 8, 8, false),
+    /*16*/ CUADMM_VARIANT(128, 4, 12, false),
 };
 static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 static const int kGlobalKind = -1;
@@ -763,7 +764,10 @@ static const int kGlobalKind = -1;
 // profiles/jacobi_tuning_r01.md; CUADMM_JACOBI_CLASSES="16:0,32:1,..." overrides it (tuning only).
 struct SizeClass { int nmax; int variant; };
 static std::vector<SizeClass> size_classes() {
-    std::vector<SizeClass> t = {{16, 0}, {32, 1}, {64, 3}, {96, 11}, {128, 8}, {168, 13}};
+    // 33..48 on 12 rows per lane instead of 16 (late round 2): the row loops are unrolled to the class's largest block, so a
+    // block of 40 issued 16 predicated row steps per rotation; measured on the C2b mix 0.469 -> 0.455 ms at drift 1e-2
+    // (96 threads for that class, or further classes at 24 / 56, were slower or equal)
+    std::vector<SizeClass> t = {{16, 0}, {32, 1}, {48, 16}, {64, 3}, {96, 11}, {128, 8}, {168, 13}};
     const char* env = getenv("CUADMM_JACOBI_CLASSES");
     if (env && *env) {
         std::vector<SizeClass> u;
