@@ -3,6 +3,7 @@
 // and the svec<->smat kernels on the reference's pooled layout.
 #include "plan.h"
 #include <algorithm>
+#include <type_traits>
 #include <numeric>
 #include <stdlib.h>
 #include <string.h>
@@ -347,48 +348,62 @@ __global__ void __launch_bounds__(T, jacobi_min_ctas(T)) proj_jacobi_kernel(Proj
         if (a.use_gram && jacobi_gram_converged<NT, WARP>(G, w, n, ld, thr2, tid)) { converged = true; break; }
         if (sweeps >= a.max_sweeps) break;
         int big = 0;
-        for (int step = 0; step < m - 1; ++step) {
-            for (int k = grp; k < half; k += NG) {
-                int pa, pb;
-                rr_pair(m, step, k, pa, pb);
-                if (pa >= n || pb >= n) continue;  // the bye of an odd-sized block
-                const int p = min(pa, pb), q = max(pa, pb);
-                double* __restrict__ Gp = G + p * ld;
-                double* __restrict__ Gq = G + q * ld;
-                double gp[RPL], gq[RPL];
-                double ga = 0.0, gb = 0.0;
-#pragma unroll
-                for (int i = 0; i < RPL; ++i) {
-                    const int r = lane + i * L;
-                    if (r < n) {
-                        gp[i] = Gp[r];
-                        gq[i] = Gq[r];
-                        if (i & 1) gb = fma(gp[i], gq[i], gb); else ga = fma(gp[i], gq[i], ga);
-                    } else {
-                        gp[i] = 0.0; gq[i] = 0.0;
-                    }
-                }
-                ga += gb;
-                const double al = w[p], be = w[q];
-#pragma unroll
-                for (int o = L / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(gmask, ga, o);
-                const double g2 = ga * ga, ab = al * be;
-                if (g2 > thr2 * ab) big = 1;
-                if (g2 > tiny2 * ab) {
-                    double c, sn, an, bn;
-                    jacobi_cs2(al, be, ga, c, sn, an, bn);
-#pragma unroll
-                    for (int i = 0; i < RPL; ++i) {
+        // The row loops are unrolled and the columns of a pair live in registers, so their trip count is a compile-time
+        // constant; a block smaller than its class's largest (n = 36 in the class up to 48) would issue the predicated
+        // row steps of the largest one.  Four instantiations per kernel, picked by the block's own row count.
+        auto run_steps = [&](auto nit_c) {
+            constexpr int NIT = decltype(nit_c)::value;
+            for (int step = 0; step < m - 1; ++step) {
+                for (int k = grp; k < half; k += NG) {
+                    int pa, pb;
+                    rr_pair(m, step, k, pa, pb);
+                    if (pa >= n || pb >= n) continue;  // the bye of an odd-sized block
+                    const int p = min(pa, pb), q = max(pa, pb);
+                    double* __restrict__ Gp = G + p * ld;
+                    double* __restrict__ Gq = G + q * ld;
+                    double gp[NIT], gq[NIT];
+                    double ga = 0.0, gb = 0.0;
+    #pragma unroll
+                    for (int i = 0; i < NIT; ++i) {
                         const int r = lane + i * L;
                         if (r < n) {
-                            Gp[r] = fma(c, gp[i], -sn * gq[i]);
-                            Gq[r] = fma(sn, gp[i], c * gq[i]);
+                            gp[i] = Gp[r];
+                            gq[i] = Gq[r];
+                            if (i & 1) gb = fma(gp[i], gq[i], gb); else ga = fma(gp[i], gq[i], ga);
+                        } else {
+                            gp[i] = 0.0; gq[i] = 0.0;
                         }
                     }
-                    if (lane == 0) { w[p] = an; w[q] = bn; }
+                    ga += gb;
+                    const double al = w[p], be = w[q];
+    #pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(gmask, ga, o);
+                    const double g2 = ga * ga, ab = al * be;
+                    if (g2 > thr2 * ab) big = 1;
+                    if (g2 > tiny2 * ab) {
+                        double c, sn, an, bn;
+                        jacobi_cs2(al, be, ga, c, sn, an, bn);
+    #pragma unroll
+                        for (int i = 0; i < NIT; ++i) {
+                            const int r = lane + i * L;
+                            if (r < n) {
+                                Gp[r] = fma(c, gp[i], -sn * gq[i]);
+                                Gq[r] = fma(sn, gp[i], c * gq[i]);
+                            }
+                        }
+                        if (lane == 0) { w[p] = an; w[q] = bn; }
+                    }
                 }
+                mat_sync<WARP>();
             }
-            mat_sync<WARP>();
+        };
+        {
+            constexpr int S = RPL >= 8 ? RPL / 8 : 1;
+            const int nit = (n + L - 1) / L;
+            if (nit <= RPL - 3 * S) run_steps(std::integral_constant<int, RPL - 3 * S>{});
+            else if (nit <= RPL - 2 * S) run_steps(std::integral_constant<int, RPL - 2 * S>{});
+            else if (nit <= RPL - S) run_steps(std::integral_constant<int, RPL - S>{});
+            else run_steps(std::integral_constant<int, RPL>{});
         }
         ++sweeps;
         if (!a.use_gram) {
@@ -764,10 +779,9 @@ static const int kGlobalKind = -1;
 // profiles/jacobi_tuning_r01.md; CUADMM_JACOBI_CLASSES="16:0,32:1,..." overrides it (tuning only).
 struct SizeClass { int nmax; int variant; };
 static std::vector<SizeClass> size_classes() {
-    // 33..48 on 12 rows per lane instead of 16 (late round 2): the row loops are unrolled to the class's largest block, so a
-    // block of 40 issued 16 predicated row steps per rotation; measured on the C2b mix 0.469 -> 0.455 ms at drift 1e-2
-    // (96 threads for that class, or further classes at 24 / 56, were slower or equal)
-    std::vector<SizeClass> t = {{16, 0}, {32, 1}, {48, 16}, {64, 3}, {96, 11}, {128, 8}, {168, 13}};
+    // (a separate class for 33..48 on 12 rows per lane was 3 % faster before the sweep was instantiated per row count, and
+    // slower after: more distinct kernels running side by side)
+    std::vector<SizeClass> t = {{16, 0}, {32, 1}, {64, 3}, {96, 11}, {128, 8}, {168, 13}};
     const char* env = getenv("CUADMM_JACOBI_CLASSES");
     if (env && *env) {
         std::vector<SizeClass> u;
