@@ -6,7 +6,7 @@
 // Shape of the data: SPOT/moment matrices have ~2-5 non-zeros per constraint row, At has many
 // empty rows and a handful of very long ones (a shared moment entry used by thousands of
 // constraints).  So: G lanes per row (G from the mean row length) for ordinary rows, and one warp
-// per "long" row (> kLongRow non-zeros) appended to the same grid.  HBM-bound: 12 B per non-zero
+// per "long" row (> kLongRow non-zeros; > 16 for the large one-lane-per-row operators) appended to the same grid.  HBM-bound: 12 B per non-zero
 // (value + int32 column), coalesced across the lanes of a group.
 #include "spmv.h"
 #include <algorithm>
